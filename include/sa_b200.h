@@ -1,0 +1,114 @@
+/*
+ * sa_b200.h -- C ABI of the B200 (sm_100a) NTT + FRI engine that stands in for the
+ * hot path of aszepieniec/stark-anatomy (code/ntt.py, code/fri.py, code/merkle.py).
+ *
+ * The reference is pure Python and has no FFI: its boundary is the Python module
+ * surface.  The entry points below are what a ctypes
+ * binding for that path binds; stark-anatomy_b200/sa_engine.py is that binding
+ * and INTEGRATION.md shows the stub a maintainer would add to the reference.
+ *
+ * Conventions
+ *  - One field element = 16 bytes: two little-endian uint64 limbs (lo, hi) of the
+ *    canonical residue in [0, p), p = 1 + 407 * 2^119 (code/algebra.py:96-98).
+ *  - Scalars (roots, offsets, challenges) are passed as `const uint64_t x[2]`.
+ *  - `void *` data pointers are DEVICE pointers unless the function name ends in
+ *    `_host`; `stream` is a cudaStream_t (NULL = default stream).  Calls are
+ *    asynchronous on `stream` unless stated otherwise.
+ *  - Return value: 0 on success, otherwise one of the SA_E* codes; the Python
+ *    binding turns SA_E* into the AssertionError (with the reference's message)
+ *    the corresponding reference function raises.
+ *  - No torch types, no C++ types: plain pointers and sizes.
+ *  - Thread safety: entry points may be called from several host threads; the
+ *    twiddle/plan caches are guarded by a mutex.  Work submitted to different
+ *    streams is independent.
+ */
+#ifndef SA_B200_H
+#define SA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SA_OK = 0,
+    SA_ENOTPOW2 = -1,   /* ntt.py:4   "cannot compute ntt of non-power-of-two sequence" */
+    SA_EROOTORDER = -2, /* ntt.py:10  "primitive root must be nth root of unity, where n is len(values)" */
+    SA_ENOTPRIM = -3,   /* ntt.py:11  "primitive root is not primitive nth root of unity, ..." */
+    SA_EDIVZERO = -4,   /* algebra.py:92 "divide by zero" (element-wise division, ntt.py:172) */
+    SA_EINDEX = -5,     /* merkle.py:18 "cannot open invalid index" */
+    SA_ESIZE = -6,      /* unsupported size (log_n > 30, n == 0, ...) */
+    SA_ECUDA = -100     /* CUDA runtime error; sa_last_error() has the text */
+};
+
+/* Version / build info, e.g. "sa_b200 0.1 sm_100a". */
+const char *sa_version(void);
+/* Text of the last CUDA error seen by this thread's calls (empty string if none). */
+const char *sa_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t sa_launch_count(void);
+
+/* ---- code/ntt.py:3-18 ntt, code/ntt.py:20-30 intt -------------------------------------
+ * out[b][i] = sum_j in[b][j] * root^(i*j), natural order in and out, for `batch`
+ * contiguous transforms of n = 2^log_n elements.  inverse != 0 computes intt: the
+ * transform with root^-1 followed by the multiplication with n^-1.
+ * Validates root^n == 1 and root^(n/2) != 1 exactly like the reference's asserts.
+ * in == out is allowed.  log_n in [0, 30].                                              */
+int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
+           void *stream);
+/* Same through HOST buffers: H2D copy, transforms, D2H copy, synchronises before
+ * returning (the end-to-end call bench.py times as `e2e`).                               */
+int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,
+                size_t batch, void *stream);
+
+/* ---- element-wise pieces of fast_multiply / fast_coset_divide / fast_coset_evaluate ---- */
+/* code/ntt.py:61  out[i] = a[i] * b[i]                                                   */
+int sa_pointwise_mul(void *out, const void *a, const void *b, size_t n, void *stream);
+/* code/ntt.py:172 out[i] = a[i] / b[i]; SA_EDIVZERO if some b[i] == 0 (synchronises).    */
+int sa_pointwise_div(void *out, const void *a, const void *b, size_t n, void *stream);
+/* code/univariate.py:153-154 as used at ntt.py:133,159-160,176: out[i] = in[i] * factor^i */
+int sa_scale(void *out, const void *in, size_t n, const uint64_t factor[2], void *stream);
+/* code/univariate.py:130-136 at many points (fast_evaluate's values, ntt.py:82-100):
+ * out[j] = sum_i coeffs[i] * points[j]^i                                                 */
+int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
+                 void *stream);
+
+/* ---- code/merkle.py:6-14 Merkle.commit -------------------------------------------------
+ * Builds the whole blake2b-512 tree over n = 2^k leaves, leaf = H(decimal ASCII of the
+ * value), node = H(left || right).  `tree` receives 2n nodes of 64 bytes in heap order:
+ * node 1 is the root, node i has children 2i and 2i+1, leaf j is node n + j, node 0 is
+ * unused.                                                                                 */
+int sa_merkle_tree(void *tree, const void *values, size_t n, void *stream);
+/* code/merkle.py:16-27 Merkle.open for k leaf indices (HOST array): paths_out receives
+ * k * log2(n) digests of 64 bytes, siblings bottom-up per index (device memory).          */
+int sa_merkle_open(void *paths_out, const void *tree, size_t n, const uint64_t *indices_host, size_t k,
+                   void *stream);
+/* out[i] = values[indices[i]] (the leaf triples of code/fri.py:104-105).                  */
+int sa_gather(void *out, const void *values, size_t n, const uint64_t *indices_host, size_t k,
+              void *stream);
+
+/* ---- code/fri.py:85 split-and-fold, and the fused round of Fri.commit (fri.py:64-88) ----
+ * next[i] = 2^-1 * ((1 + alpha/(offset*omega^i)) * cw[i] + (1 - alpha/(offset*omega^i)) * cw[n/2+i])
+ * for i < n/2.  sa_fri_round additionally builds the Merkle tree of `next` (n/2 leaves,
+ * n nodes of 64 bytes) in the same kernel that folds; sa_fri_fold only folds.             */
+int sa_fri_fold(void *next, const void *cw, size_t n, const uint64_t alpha[2], const uint64_t offset[2],
+                const uint64_t omega[2], void *stream);
+int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const uint64_t alpha[2],
+                 const uint64_t offset[2], const uint64_t omega[2], void *stream);
+
+/* ---- self checks (used by tests / smoke) ------------------------------------------------
+ * Runs the sm_100a carry-chain field arithmetic against the portable C++ version on
+ * `count` pseudo-random pairs (plus edge cases) on the device; returns the number of
+ * mismatches (0 = pass) or a negative SA_E* code.                                         */
+long long sa_selftest_field(size_t count, uint64_t seed);
+/* Micro-benchmark: n_threads threads each run `iters` dependent rounds of `ilp`
+ * independent operations of kind op (0 montmul, 1 add, 2 sub, 3 butterfly).  Returns the
+ * kernel time in milliseconds (negative on error).                                        */
+double sa_microbench(int op, int ilp, int iters, int blocks, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_B200_H */

@@ -1,0 +1,200 @@
+// hash.cuh -- blake2b-512 single-block compression and the decimal-ASCII leaf
+// encoding, as the reference's Merkle tree uses them:
+//   leaf  = blake2b(str(value).encode())          code/merkle.py:13-14, code/algebra.py:53-57
+//   node  = blake2b(left || right)                code/merkle.py:6-11
+// A leaf message is 1..39 bytes and a node message exactly 128 bytes, so both
+// are ONE compression of the final block (RFC 7693; hashlib.blake2b defaults:
+// 64-byte digest, no key, fanout = depth = 1).
+// __host__ __device__ so tests/emu can run the same code on the CPU.
+#pragma once
+#include "field.cuh"
+
+namespace sa {
+
+SA_HD uint64_t b2_rotr(uint64_t x, int r) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (r == 32) return ((uint64_t)lo << 32) | hi;
+    if (r == 24) {
+        // bytes of (hi:lo) rotated right by 3
+        uint32_t nlo = __byte_perm(lo, hi, 0x6543), nhi = __byte_perm(lo, hi, 0x2107);
+        return ((uint64_t)nhi << 32) | nlo;
+    }
+    if (r == 16) {
+        uint32_t nlo = __byte_perm(lo, hi, 0x5432), nhi = __byte_perm(lo, hi, 0x1076);
+        return ((uint64_t)nhi << 32) | nlo;
+    }
+    // r == 63: rotate left by one
+    uint32_t nlo = __funnelshift_l(hi, lo, 1), nhi = __funnelshift_l(lo, hi, 1);
+    return ((uint64_t)nhi << 32) | nlo;
+#else
+    return (x >> r) | (x << (64 - r));
+#endif
+}
+
+#define SA_B2_G(a, b, c, d, x, y)   \
+    do {                            \
+        a = a + b + (x);            \
+        d = b2_rotr(d ^ a, 32);     \
+        c = c + d;                  \
+        b = b2_rotr(b ^ c, 24);     \
+        a = a + b + (y);            \
+        d = b2_rotr(d ^ a, 16);     \
+        c = c + d;                  \
+        b = b2_rotr(b ^ c, 63);     \
+    } while (0)
+
+#define SA_B2_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    do {                                                                                   \
+        SA_B2_G(v0, v4, v8, v12, m[s0], m[s1]);                                            \
+        SA_B2_G(v1, v5, v9, v13, m[s2], m[s3]);                                            \
+        SA_B2_G(v2, v6, v10, v14, m[s4], m[s5]);                                           \
+        SA_B2_G(v3, v7, v11, v15, m[s6], m[s7]);                                           \
+        SA_B2_G(v0, v5, v10, v15, m[s8], m[s9]);                                           \
+        SA_B2_G(v1, v6, v11, v12, m[s10], m[s11]);                                         \
+        SA_B2_G(v2, v7, v8, v13, m[s12], m[s13]);                                          \
+        SA_B2_G(v3, v4, v9, v14, m[s14], m[s15]);                                          \
+    } while (0)
+
+// digest (8 words) of a message that fits one 128-byte block; len = message bytes,
+// m[] zero padded.  h0 = IV ^ parameter block (0x01010040 into word 0).
+SA_HD void blake2b_single_block(uint64_t out[8], const uint64_t m[16], uint32_t len) {
+    const uint64_t iv0 = 0x6a09e667f3bcc908ULL, iv1 = 0xbb67ae8584caa73bULL, iv2 = 0x3c6ef372fe94f82bULL,
+                   iv3 = 0xa54ff53a5f1d36f1ULL, iv4 = 0x510e527fade682d1ULL, iv5 = 0x9b05688c2b3e6c1fULL,
+                   iv6 = 0x1f83d9abfb41bd6bULL, iv7 = 0x5be0cd19137e2179ULL;
+    const uint64_t h0 = iv0 ^ 0x01010040ULL;
+    uint64_t v0 = h0, v1 = iv1, v2 = iv2, v3 = iv3, v4 = iv4, v5 = iv5, v6 = iv6, v7 = iv7;
+    uint64_t v8 = iv0, v9 = iv1, v10 = iv2, v11 = iv3, v12 = iv4 ^ (uint64_t)len, v13 = iv5, v14 = ~iv6,
+             v15 = iv7;
+    SA_B2_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    SA_B2_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    SA_B2_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4);
+    SA_B2_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8);
+    SA_B2_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13);
+    SA_B2_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9);
+    SA_B2_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11);
+    SA_B2_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10);
+    SA_B2_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5);
+    SA_B2_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0);
+    SA_B2_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    SA_B2_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3);
+    out[0] = h0 ^ v0 ^ v8;
+    out[1] = iv1 ^ v1 ^ v9;
+    out[2] = iv2 ^ v2 ^ v10;
+    out[3] = iv3 ^ v3 ^ v11;
+    out[4] = iv4 ^ v4 ^ v12;
+    out[5] = iv5 ^ v5 ^ v13;
+    out[6] = iv6 ^ v6 ^ v14;
+    out[7] = iv7 ^ v7 ^ v15;
+}
+
+// str(value).encode(): decimal ASCII, most significant digit first, no leading
+// zeros ("0" for zero), packed little-endian into w[0..4] (40 bytes, zero padded).
+// Returns the length in bytes (1..39).   code/algebra.py:53-57
+SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
+    // base-1e9 limbs, least significant first; 2^128 < 1e39 so five limbs (9,9,9,9,3 digits)
+    uint32_t q[4] = {x.v[0], x.v[1], x.v[2], x.v[3]};
+    uint32_t chunk[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 5; k++) {
+        uint64_t rem = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 3; i >= 0; i--) {
+            const uint64_t cur = (rem << 32) | q[i];
+            const uint64_t d = cur / 1000000000ULL;
+            q[i] = (uint32_t)d;
+            rem = cur - d * 1000000000ULL;
+        }
+        chunk[k] = (uint32_t)rem;
+    }
+    // 48 character slots, right aligned: slots 3..47 hold the 45 zero-padded digits
+    // (slot index = byte index in the 6-word buffer below)
+    uint64_t buf[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t nd = 1;  // significant digits
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 5; k++) {
+        uint32_t cval = chunk[k];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 9; j++) {
+            const uint32_t nq = cval / 10u;
+            const uint32_t dig = cval - nq * 10u;
+            cval = nq;
+            const int pos = 9 * k + j;  // decimal position, 0 = units
+            if (dig != 0) nd = (uint32_t)pos + 1;
+            const int slot = 47 - pos;
+            buf[slot >> 3] |= (uint64_t)(dig + 48u) << (8 * (slot & 7));
+        }
+    }
+    // drop the leading (48 - nd) bytes: out byte i = buf byte (48 - nd + i)
+    const uint32_t lz = 48u - nd;
+    const uint32_t ws = lz >> 3, bs = (lz & 7u) * 8u;
+    uint64_t t[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; i++) t[i] = buf[i];
+    t[6] = 0;
+    // whole-word shift by ws in {0..5} as three conditional stages (1, 2, 4 words)
+    if (ws & 1u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 6; i++) t[i] = t[i + 1];
+    }
+    if (ws & 2u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 6; i++) t[i] = (i + 2 < 7) ? t[i + 2] : 0;
+    }
+    if (ws & 4u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 6; i++) t[i] = (i + 4 < 7) ? t[i + 4] : 0;
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 5; i++) {
+        const uint64_t lo = t[i] >> bs;
+        const uint64_t hi = bs ? (t[i + 1] << (64u - bs)) : 0;
+        w[i] = lo | hi;
+    }
+    // bytes at and beyond nd must be zero (they are: the buffer ends at slot 47)
+    return nd;
+}
+
+// leaf digest of one field element
+SA_HD void merkle_leaf_digest(uint64_t out[8], const fe &x) {
+    uint64_t m[16];
+    const uint32_t len = fe_decimal_words(m, x);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 5; i < 16; i++) m[i] = 0;
+    blake2b_single_block(out, m, len);
+}
+
+// node digest of two child digests
+SA_HD void merkle_node_digest(uint64_t out[8], const uint64_t left[8], const uint64_t right[8]) {
+    uint64_t m[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) {
+        m[i] = left[i];
+        m[8 + i] = right[i];
+    }
+    blake2b_single_block(out, m, 128u);
+}
+
+}  // namespace sa

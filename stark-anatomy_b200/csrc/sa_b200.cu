@@ -1,0 +1,680 @@
+// sa_b200.cu -- kernels and C ABI (include/sa_b200.h) of the B200 NTT + FRI engine.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//
+// Reference behaviour reproduced (bit-exact): code/ntt.py:3-30,61,133,172, code/fri.py:85,
+// code/merkle.py:6-27, code/algebra.py:53-57,75-94.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/sa_b200.h"
+#include "field.cuh"
+#include "fri_merkle.cuh"
+#include "hash.cuh"
+#include "ntt_plan.cuh"
+#include "ntt_tile.cuh"
+
+using namespace sa;
+
+// ------------------------------------------------------------------ plumbing --
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+#define SA_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            return SA_ECUDA;                                                                   \
+        }                                                                                      \
+    } while (0)
+#define SA_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            g_last_error = std::string("kernel launch: ") + cudaGetErrorString(_e);            \
+            return SA_ECUDA;                                                                   \
+        }                                                                                      \
+    } while (0)
+
+static inline fe fe_from_limbs(const uint64_t x[2]) {
+    return fe_make((uint32_t)x[0], (uint32_t)(x[0] >> 32), (uint32_t)x[1], (uint32_t)(x[1] >> 32));
+}
+static inline bool host_is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline int host_log2(size_t n) {
+    int l = 0;
+    while ((size_t(1) << l) < n) l++;
+    return l;
+}
+
+// ------------------------------------------------------------------- kernels --
+template <int LOGL>
+__global__ void __launch_bounds__(TilePlan<LOGL>::TPT *TilePlan<LOGL>::TPC)
+    ntt_tile_kernel(const __grid_constant__ TileArgs a, long long total_tiles, int tiles_per_batch) {
+    using P = TilePlan<LOGL>;
+    extern __shared__ uint4 sa_smem_u4[];
+    fe *smem = reinterpret_cast<fe *>(sa_smem_u4);
+    const int tic = threadIdx.x / P::TPT, t = threadIdx.x % P::TPT;
+    const long long tile = (long long)blockIdx.x * P::TPC + tic;
+    const bool valid = tile < total_tiles;
+    const long long b = valid ? tile / tiles_per_batch : 0;
+    const int col0 = valid ? (int)(tile % tiles_per_batch) * TILE_C : 0;
+    fe *sm = smem + (size_t)tic * P::L * TILE_C;
+    ntt_tile_stage<LOGL, 0>(t, sm, a, b, col0, valid);
+    if constexpr (P::NST > 1) {
+        __syncthreads();
+        ntt_tile_stage<LOGL, 1>(t, sm, a, b, col0, valid);
+    }
+    if constexpr (P::NST > 2) {
+        __syncthreads();
+        ntt_tile_stage<LOGL, 2>(t, sm, a, b, col0, valid);
+    }
+}
+
+// out[e] = base^e * lead (Montgomery form) for e < count; 16 consecutive powers per thread
+__global__ void k_pow_table(fe *out, fe base_m, fe lead_m, long long count) {
+    const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (e0 >= count) return;
+    fe acc = fe_montmul(fe_mont_pow_u64(base_m, (uint64_t)e0), lead_m);
+    for (int i = 0; i < 16 && e0 + i < count; i++) {
+        tile_st(out + e0 + i, acc);
+        acc = fe_montmul(acc, base_m);
+    }
+}
+// out[k * n2 + j] = w^(k*j) * scale (Montgomery form): row k is the power table of w^k
+__global__ void k_twb_table(fe *out, fe w_m, fe scale_m, int n1, int n2) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_row = (n2 + 15) / 16;
+    const long long k = idx / per_row;
+    const long long j0 = (idx % per_row) * 16;
+    if (k >= n1) return;
+    const fe wk = fe_mont_pow_u64(w_m, (uint64_t)k);
+    fe acc = fe_montmul(fe_mont_pow_u64(wk, (uint64_t)j0), scale_m);
+    for (int i = 0; i < 16 && j0 + i < n2; i++) {
+        tile_st(out + k * n2 + j0 + i, acc);
+        acc = fe_montmul(acc, wk);
+    }
+}
+
+__global__ void k_pointwise_mul(fe *out, const fe *a, const fe *b, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        tile_st(out + i, fe_montmul(fe_to_mont(tile_ld(a + i)), tile_ld(b + i)));
+}
+// out = a / b with Montgomery's batch-inversion trick over 8 strided elements per thread
+__global__ void k_pointwise_div(fe *out, const fe *a, const fe *b, long long n, int *zero_flag) {
+    constexpr int G = 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long base = i0; base < n; base += stride * G) {
+        fe bm[G], pre[G];
+        fe acc = fe_mont_one();
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const long long i = base + g * stride;
+            fe v = (i < n) ? tile_ld(b + i) : fe_one();
+            if (fe_is_zero(v)) {
+                *zero_flag = 1;
+                v = fe_one();
+            }
+            bm[g] = fe_to_mont(v);
+            pre[g] = acc;
+            acc = fe_montmul(acc, bm[g]);
+        }
+        fe inv = fe_mont_inv(acc);
+#pragma unroll
+        for (int g = G - 1; g >= 0; g--) {
+            const long long i = base + g * stride;
+            const fe binv = fe_montmul(inv, pre[g]);  // Montgomery form of 1/b[i]
+            inv = fe_montmul(inv, bm[g]);
+            if (i < n) tile_st(out + i, fe_montmul(tile_ld(a + i), binv));
+        }
+    }
+}
+// out[i] = in[i] * factor^i; thread handles i, i + T, i + 2T, ... with running factor^T
+__global__ void k_scale(fe *out, const fe *in, long long n, fe factor_m, fe factor_T_m) {
+    const long long T = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe f = fe_mont_pow_u64(factor_m, (uint64_t)i);
+    for (; i < n; i += T) {
+        tile_st(out + i, fe_montmul(tile_ld(in + i), f));
+        f = fe_montmul(f, factor_T_m);
+    }
+}
+// Horner, one thread per point (coefficients are read through the read-only path, broadcast)
+__global__ void k_poly_eval(fe *out, const fe *coeffs, long long ncoef, const fe *points, long long npts) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    const fe x_m = fe_to_mont(tile_ld(points + j));
+    fe acc = fe_zero();
+    for (long long i = ncoef - 1; i >= 0; i--) acc = fe_add(fe_montmul(acc, x_m), tile_ldg(coeffs + i));
+    tile_st(out + j, acc);
+}
+__global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xinv, fe s_m, fe inv2_m) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+        const fe t_m = fe_montmul(tile_ldg(xinv + i), s_m);
+        tile_st(next + i, fri_fold_one(tile_ld(cw + i), tile_ld(cw + half + i), t_m, inv2_m));
+    }
+}
+
+// One CTA reduces `chunk` bottom nodes to one node, writing every level to the heap-ordered tree.
+// mode 2 is the fused FRI round: fold -> leaf digest -> subtree, one pass over the codeword.
+__global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
+    __shared__ uint64_t sm[MK_CHUNK * 8];
+    const int tid = threadIdx.x;
+    const long long blk = blockIdx.x;
+    uint64_t d[8];
+    for (int j = tid; j < a.chunk; j += MK_THREADS) {
+        merkle_bottom(d, a, blk, j);
+#pragma unroll
+        for (int i = 0; i < 8; i++) sm[j * 8 + i] = d[i];
+    }
+    __syncthreads();
+    long long gw = a.width / 2;  // global width of the level being produced
+    for (int wl = a.chunk / 2; wl >= 1; wl >>= 1, gw >>= 1) {
+        const bool mine = tid < wl;
+        if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
+        __syncthreads();
+        if (mine) {
+            uint64_t *node = a.tree + (gw + blk * wl + tid) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                sm[tid * 8 + i] = d[i];
+                node[i] = d[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_merkle_paths(uint64_t *out, const uint64_t *tree, long long n, int depth,
+                               const uint64_t *indices, long long k) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = k * depth * 8;
+    if (t >= total) return;
+    const int w = (int)(t & 7);
+    const long long ql = t >> 3;
+    const int level = (int)(ql % depth);
+    const long long q = ql / depth;
+    const long long node = ((n + (long long)indices[q]) >> level) ^ 1;
+    out[t] = tree[node * 8 + w];
+}
+__global__ void k_gather(fe *out, const fe *values, const uint64_t *indices, long long k) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < k) tile_st(out + t, tile_ld(values + indices[t]));
+}
+
+// --- self test: PTX carry-chain field ops vs the portable C++ ones -------------------------
+__device__ __forceinline__ uint64_t sa_splitmix(uint64_t &s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ fe sa_rand_fe(uint64_t &s, int kind) {
+    const uint64_t a = sa_splitmix(s), b = sa_splitmix(s);
+    fe r = fe_make((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    switch (kind & 15) {  // edge cases
+        case 0: r = fe_zero(); break;
+        case 1: r = fe_one(); break;
+        case 2: r = fe_make(0, 0, 0, P3); break;                                  // p - 1
+        case 3: r = fe_make(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, P3 - 1); break;  // p - 2
+        case 4: r.v[3] = P3; r.v[2] = 0; r.v[1] = 0; r.v[0] = 0; break;
+        case 5: r.v[0] = 0; break;
+        case 6: r.v[0] = 0; r.v[1] = 0; r.v[2] = 0; break;
+        default: break;
+    }
+    // canonicalise: force below p
+    if (r.v[3] > P3 || (r.v[3] == P3 && (r.v[2] | r.v[1] | r.v[0]) != 0)) r.v[3] -= P3;
+    return r;
+}
+__global__ void k_selftest_field(unsigned long long *mismatches, long long count, uint64_t seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t s = seed + 0x1234567ULL * (uint64_t)i;
+    const fe a = sa_rand_fe(s, (int)(i % 37)), b = sa_rand_fe(s, (int)((i / 37) % 41));
+    int bad = 0;
+    bad += !fe_eq(fe_add(a, b), fe_add_portable(a, b));
+    bad += !fe_eq(fe_sub(a, b), fe_sub_portable(a, b));
+    bad += !fe_eq(fe_montmul(a, b), fe_montmul_portable(a, b));
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+template <int OP, int ILP>
+__global__ void k_microbench(fe *sink, int iters) {
+    fe x[ILP], y[ILP];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) {
+        x[i] = fe_make(t + i, t * 3 + 1, i + 7, 0x12345678u + i);
+        y[i] = fe_make(t * 5 + i, t + 11, i + 3, 0x0ABCDEF0u + i);
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) {
+            if (OP == 0) x[i] = fe_montmul(x[i], y[i]);
+            if (OP == 1) x[i] = fe_add(x[i], y[i]);
+            if (OP == 2) x[i] = fe_sub(x[i], y[i]);
+            if (OP == 3) {
+                const fe tt = fe_montmul(y[i], x[(i + 1) % ILP]);
+                const fe e = x[i];
+                x[i] = fe_add(e, tt);
+                y[i] = fe_sub(e, tt);
+            }
+        }
+    }
+    fe acc = x[0];
+#pragma unroll
+    for (int i = 1; i < ILP; i++) acc = fe_add(acc, fe_add(x[i], y[i]));
+    if (acc.v[0] == 0xDEADBEEFu && acc.v[1] == 0x1u) tile_st(sink + t, acc);
+}
+
+// ---------------------------------------------------------------- NTT plans --
+struct NttPlan {
+    int log_n = 0, l1 = 0, l2 = 0;
+    fe *tw1 = nullptr, *tw2 = nullptr, *twb = nullptr;
+    fe cst1[8], cst2[8];
+    fe scale_m;     // n^-1 (Montgomery) for single-tile inverse transforms
+    int has_scale = 0;
+};
+using PlanKey = std::tuple<int, int, uint64_t, uint64_t, int>;  // device, log_n, root lo, root hi, inverse
+static std::mutex g_plan_mu;
+static std::map<PlanKey, NttPlan> g_plans;
+
+static int build_pow_table(fe **out, const fe &base_m, const fe &lead_m, long long count, cudaStream_t st) {
+    SA_CUDA(cudaMalloc(out, sizeof(fe) * (size_t)count));
+    const long long threads = (count + 15) / 16;
+    const int bs = 128;
+    k_pow_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(*out, base_m, lead_m, count);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+// validates the root like ntt.py:10-11 and returns (creating if needed) the plan
+static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, cudaStream_t st) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    const uint64_t rlo = (uint64_t)root.v[0] | ((uint64_t)root.v[1] << 32);
+    const uint64_t rhi = (uint64_t)root.v[2] | ((uint64_t)root.v[3] << 32);
+    const PlanKey key(dev, log_n, rlo, rhi, inverse ? 1 : 0);
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) {
+        *plan_out = &it->second;
+        return SA_OK;
+    }
+    const uint64_t n = 1ull << log_n;
+    const fe root_m = fe_to_mont(root);
+    if (!fe_eq(fe_mont_pow_u64(root_m, n), fe_mont_one())) return SA_EROOTORDER;
+    if (fe_eq(fe_mont_pow_u64(root_m, n / 2), fe_mont_one())) return SA_ENOTPRIM;
+    // the transform root: root itself, or root^-1 for intt (ntt.py:29)
+    const fe w_m = inverse ? fe_mont_inv(root_m) : root_m;
+    const fe ninv_m = fe_mont_inv(fe_to_mont(fe_from_u64(n)));  // ntt.py:27
+    NttPlan p;
+    p.log_n = log_n;
+    int rc;
+    const NttShape shape = ntt_shape(log_n);
+    p.l1 = shape.l1;
+    p.l2 = shape.l2;
+    if (log_n <= 10) {
+        if ((rc = build_pow_table(&p.tw1, w_m, fe_mont_one(), (long long)n, st)) != SA_OK) return rc;
+        ntt_fill_cst(p.cst1, w_m, (int)n);
+        p.has_scale = inverse ? 1 : 0;
+        p.scale_m = inverse ? ninv_m : fe_mont_one();
+    } else {
+        const int n1 = 1 << p.l1, n2 = 1 << p.l2;
+        const fe w1_m = fe_mont_pow_u64(w_m, (uint64_t)n2);  // root of the length-n1 column transforms
+        const fe w2_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-n2 row transforms
+        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st)) != SA_OK) return rc;
+        ntt_fill_cst(p.cst1, w1_m, n1);
+        ntt_fill_cst(p.cst2, w2_m, n2);
+        SA_CUDA(cudaMalloc(&p.twb, sizeof(fe) * (size_t)n));
+        const long long threads = (long long)n1 * ((n2 + 15) / 16);
+        const int bs = 128;
+        k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(
+            p.twb, w_m, inverse ? ninv_m : fe_mont_one(), n1, n2);
+        SA_LAUNCH_CHECK();
+    }
+    auto ins = g_plans.emplace(key, p);
+    *plan_out = &ins.first->second;
+    return SA_OK;
+}
+
+template <int LOGL>
+static int launch_tile(const TileArgs &a, cudaStream_t st) {
+    using P = TilePlan<LOGL>;
+    const int tiles_per_batch = (a.ncols + TILE_C - 1) / TILE_C;
+    const long long total = (long long)tiles_per_batch * a.nbatch;
+    const long long grid = (total + P::TPC - 1) / P::TPC;
+    const size_t smem = P::smem_bytes();
+    static bool attr_done = false;
+    if (smem > 48 * 1024 && !attr_done) {
+        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        attr_done = true;
+    }
+    ntt_tile_kernel<LOGL><<<(unsigned)grid, P::TPT * P::TPC, smem, st>>>(a, total, tiles_per_batch);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+static int launch_tile_dyn(int logl, const TileArgs &a, cudaStream_t st) {
+    switch (logl) {
+        case 1: return launch_tile<1>(a, st);
+        case 2: return launch_tile<2>(a, st);
+        case 3: return launch_tile<3>(a, st);
+        case 4: return launch_tile<4>(a, st);
+        case 5: return launch_tile<5>(a, st);
+        case 6: return launch_tile<6>(a, st);
+        case 7: return launch_tile<7>(a, st);
+        case 8: return launch_tile<8>(a, st);
+        case 9: return launch_tile<9>(a, st);
+        case 10: return launch_tile<10>(a, st);
+    }
+    return SA_ESIZE;
+}
+
+// ------------------------------------------------------------------- C ABI --
+extern "C" {
+
+const char *sa_version(void) { return "sa_b200 0.1 sm_100a"; }
+const char *sa_last_error(void) { return g_last_error.c_str(); }
+uint64_t sa_launch_count(void) { return g_launches.load(); }
+
+int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
+           void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (log_n < 0 || log_n > 20) return SA_ESIZE;
+    if (batch == 0) return SA_OK;
+    const size_t n = size_t(1) << log_n;
+    if (log_n == 0) {  // ntt.py:5-6 / :23-24: a length-1 sequence is returned as is
+        if (out != in) SA_CUDA(cudaMemcpyAsync(out, in, 16 * batch, cudaMemcpyDeviceToDevice, st));
+        return SA_OK;
+    }
+    NttPlan *p = nullptr;
+    int rc = get_plan(&p, log_n, fe_from_limbs(root), inverse, st);
+    if (rc != SA_OK) return rc;
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    if (log_n <= 10) {
+        // every transform is one tile column; in-place is safe because a tile reads all of
+        // its columns into registers before it writes any of them
+        if (batch > (size_t)1 << 30) return SA_ESIZE;
+        ntt_fill_single(a, (const fe *)in, (fe *)out, log_n, batch, p->tw1, p->cst1, p->has_scale, p->scale_m);
+        return launch_tile_dyn(log_n, a, st);
+    }
+    NttShape shape;
+    shape.log_n = log_n;
+    shape.l1 = p->l1;
+    shape.l2 = p->l2;
+    fe *tmp = nullptr;
+    SA_CUDA(cudaMallocAsync((void **)&tmp, sizeof(fe) * n * batch, st));
+    ntt_fill_pass1(a, (const fe *)in, tmp, shape, batch, p->tw1, p->twb, p->cst1);
+    rc = launch_tile_dyn(p->l1, a, st);
+    if (rc == SA_OK) {
+        ntt_fill_pass2(a, tmp, (fe *)out, shape, batch, p->tw2, p->cst2);
+        rc = launch_tile_dyn(p->l2, a, st);
+    }
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,
+                size_t batch, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (log_n < 0 || log_n > 20) return SA_ESIZE;
+    const size_t bytes = (size_t(16) << log_n) * batch;
+    if (bytes == 0) return SA_OK;
+    void *dev = nullptr;
+    SA_CUDA(cudaMallocAsync(&dev, bytes, st));
+    SA_CUDA(cudaMemcpyAsync(dev, in_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = sa_ntt(dev, dev, log_n, root, inverse, batch, stream);
+    if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(out_host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    cudaFreeAsync(dev, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+static inline unsigned grid_for(long long n, int bs, long long cap = 148 * 16) {
+    long long g = (n + bs - 1) / bs;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+int sa_pointwise_mul(void *out, const void *a, const void *b, size_t n, void *stream) {
+    if (n == 0) return SA_OK;
+    k_pointwise_mul<<<grid_for((long long)n, 256), 256, 0, (cudaStream_t)stream>>>((fe *)out, (const fe *)a,
+                                                                                   (const fe *)b, (long long)n);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+int sa_pointwise_div(void *out, const void *a, const void *b, size_t n, void *stream) {
+    if (n == 0) return SA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int *flag = nullptr;
+    SA_CUDA(cudaMallocAsync((void **)&flag, sizeof(int), st));
+    SA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    k_pointwise_div<<<grid_for(((long long)n + 7) / 8, 128), 128, 0, st>>>((fe *)out, (const fe *)a,
+                                                                          (const fe *)b, (long long)n, flag);
+    SA_LAUNCH_CHECK();
+    int h = 0;
+    SA_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(flag, st);
+    return h ? SA_EDIVZERO : SA_OK;
+}
+
+int sa_scale(void *out, const void *in, size_t n, const uint64_t factor[2], void *stream) {
+    if (n == 0) return SA_OK;
+    const int bs = 256;
+    const unsigned grid = grid_for((long long)n, bs, 148 * 4);
+    const fe f_m = fe_to_mont(fe_from_limbs(factor));
+    const fe fT_m = fe_mont_pow_u64(f_m, (uint64_t)grid * bs);
+    k_scale<<<grid, bs, 0, (cudaStream_t)stream>>>((fe *)out, (const fe *)in, (long long)n, f_m, fT_m);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
+                 void *stream) {
+    if (npoints == 0) return SA_OK;
+    const int bs = 64;
+    k_poly_eval<<<(unsigned)((npoints + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        (fe *)out, (const fe *)coeffs, (long long)ncoef, (const fe *)points, (long long)npoints);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+// ---- Merkle / FRI ----
+static int merkle_reduce(MerkleArgs a, cudaStream_t st) {
+    // first launch handles the bottom level in a.mode, later launches continue from digests
+    while (true) {
+        a.chunk = (int)(a.width < MK_CHUNK ? a.width : MK_CHUNK);
+        k_merkle_chunk<<<(unsigned)(a.width / a.chunk), MK_THREADS, 0, st>>>(a);
+        SA_LAUNCH_CHECK();
+        if (a.width <= MK_CHUNK) break;
+        a.width /= MK_CHUNK;
+        a.mode = 0;
+    }
+    return SA_OK;
+}
+
+int sa_merkle_tree(void *tree, const void *values, size_t n, void *stream) {
+    if (!host_is_pow2(n)) return SA_ENOTPOW2;
+    cudaStream_t st = (cudaStream_t)stream;
+    SA_CUDA(cudaMemsetAsync(tree, 0, 64, st));
+    MerkleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = (uint64_t *)tree;
+    a.width = (long long)n;
+    a.mode = 1;
+    a.values = (const fe *)values;
+    return merkle_reduce(a, st);
+}
+
+int sa_merkle_open(void *paths_out, const void *tree, size_t n, const uint64_t *indices_host, size_t k,
+                   void *stream) {
+    if (!host_is_pow2(n)) return SA_ENOTPOW2;
+    for (size_t i = 0; i < k; i++)
+        if (indices_host[i] >= n) return SA_EINDEX;
+    const int depth = host_log2(n);
+    if (k == 0 || depth == 0) return SA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *idx = nullptr;
+    SA_CUDA(cudaMallocAsync((void **)&idx, 8 * k, st));
+    SA_CUDA(cudaMemcpyAsync(idx, indices_host, 8 * k, cudaMemcpyHostToDevice, st));
+    const long long total = (long long)k * depth * 8;
+    k_merkle_paths<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((uint64_t *)paths_out,
+                                                                    (const uint64_t *)tree, (long long)n,
+                                                                    depth, idx, (long long)k);
+    SA_LAUNCH_CHECK();
+    cudaFreeAsync(idx, st);
+    return SA_OK;
+}
+
+int sa_gather(void *out, const void *values, size_t n, const uint64_t *indices_host, size_t k, void *stream) {
+    for (size_t i = 0; i < k; i++)
+        if (indices_host[i] >= n) return SA_EINDEX;
+    if (k == 0) return SA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *idx = nullptr;
+    SA_CUDA(cudaMallocAsync((void **)&idx, 8 * k, st));
+    SA_CUDA(cudaMemcpyAsync(idx, indices_host, 8 * k, cudaMemcpyHostToDevice, st));
+    k_gather<<<(unsigned)((k + 127) / 128), 128, 0, st>>>((fe *)out, (const fe *)values, idx, (long long)k);
+    SA_LAUNCH_CHECK();
+    cudaFreeAsync(idx, st);
+    return SA_OK;
+}
+
+// x_i^-1 tables: xinv[i] = omega^-i (Montgomery), i < n/2, cached per (device, omega, n)
+using XinvKey = std::tuple<int, uint64_t, uint64_t, uint64_t>;
+static std::map<XinvKey, fe *> g_xinv;
+static int get_xinv(fe **out, const fe &omega, size_t n, cudaStream_t st) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    const XinvKey key(dev, (uint64_t)omega.v[0] | ((uint64_t)omega.v[1] << 32),
+                      (uint64_t)omega.v[2] | ((uint64_t)omega.v[3] << 32), (uint64_t)n);
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_xinv.find(key);
+    if (it != g_xinv.end()) {
+        *out = it->second;
+        return SA_OK;
+    }
+    const fe winv_m = fe_mont_inv(fe_to_mont(omega));
+    fe *tab = nullptr;
+    int rc = build_pow_table(&tab, winv_m, fe_mont_one(), (long long)(n / 2), st);
+    if (rc != SA_OK) return rc;
+    g_xinv[key] = tab;
+    *out = tab;
+    return SA_OK;
+}
+
+static int fri_scalars(fe *s_m, fe *inv2_m, const uint64_t alpha[2], const uint64_t offset[2]) {
+    *inv2_m = fe_mont_inv(fe_to_mont(fe_from_u64(2)));
+    const fe oinv_m = fe_mont_inv(fe_to_mont(fe_from_limbs(offset)));
+    // alpha * 2^-1 * offset^-1, Montgomery form
+    *s_m = fe_montmul(fe_montmul(fe_to_mont(fe_from_limbs(alpha)), *inv2_m), oinv_m);
+    return SA_OK;
+}
+
+int sa_fri_fold(void *next, const void *cw, size_t n, const uint64_t alpha[2], const uint64_t offset[2],
+                const uint64_t omega[2], void *stream) {
+    if (!host_is_pow2(n) || n < 2) return SA_ENOTPOW2;
+    cudaStream_t st = (cudaStream_t)stream;
+    fe *xinv = nullptr;
+    int rc = get_xinv(&xinv, fe_from_limbs(omega), n, st);
+    if (rc != SA_OK) return rc;
+    fe s_m, inv2_m;
+    fri_scalars(&s_m, &inv2_m, alpha, offset);
+    k_fri_fold<<<grid_for((long long)(n / 2), 128), 128, 0, st>>>((fe *)next, (const fe *)cw,
+                                                                 (long long)(n / 2), xinv, s_m, inv2_m);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const uint64_t alpha[2],
+                 const uint64_t offset[2], const uint64_t omega[2], void *stream) {
+    if (!host_is_pow2(n) || n < 2) return SA_ENOTPOW2;
+    cudaStream_t st = (cudaStream_t)stream;
+    fe *xinv = nullptr;
+    int rc = get_xinv(&xinv, fe_from_limbs(omega), n, st);
+    if (rc != SA_OK) return rc;
+    SA_CUDA(cudaMemsetAsync(next_tree, 0, 64, st));
+    MerkleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = (uint64_t *)next_tree;
+    a.width = (long long)(n / 2);
+    a.mode = 2;
+    a.prev = (const fe *)cw;
+    a.next = (fe *)next;
+    a.xinv = xinv;
+    fri_scalars(&a.s_m, &a.inv2_m, alpha, offset);
+    return merkle_reduce(a, st);
+}
+
+long long sa_selftest_field(size_t count, uint64_t seed) {
+    unsigned long long *d = nullptr, h = 0;
+    SA_CUDA(cudaMalloc(&d, 8));
+    SA_CUDA(cudaMemset(d, 0, 8));
+    k_selftest_field<<<(unsigned)((count + 255) / 256), 256>>>(d, (long long)count, seed);
+    SA_LAUNCH_CHECK();
+    SA_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return (long long)h;
+}
+
+}  // extern "C"
+template <int OP>
+static double microbench_op(int ilp, int iters, int blocks, int threads, fe *sink) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto run = [&](int it) {
+        switch (ilp) {
+            case 1: k_microbench<OP, 1><<<blocks, threads>>>(sink, it); break;
+            case 2: k_microbench<OP, 2><<<blocks, threads>>>(sink, it); break;
+            case 4: k_microbench<OP, 4><<<blocks, threads>>>(sink, it); break;
+            default: k_microbench<OP, 8><<<blocks, threads>>>(sink, it); break;
+        }
+    };
+    run(iters / 8 + 1);  // warm up
+    cudaEventRecord(e0);
+    run(iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)ms;
+}
+extern "C" {
+double sa_microbench(int op, int ilp, int iters, int blocks, int threads) {
+    fe *sink = nullptr;
+    if (cudaMalloc(&sink, sizeof(fe) * (size_t)blocks * threads) != cudaSuccess) return -1.0;
+    double ms = -1.0;
+    switch (op) {
+        case 0: ms = microbench_op<0>(ilp, iters, blocks, threads, sink); break;
+        case 1: ms = microbench_op<1>(ilp, iters, blocks, threads, sink); break;
+        case 2: ms = microbench_op<2>(ilp, iters, blocks, threads, sink); break;
+        case 3: ms = microbench_op<3>(ilp, iters, blocks, threads, sink); break;
+    }
+    g_launches.fetch_add(2);
+    if (cudaGetLastError() != cudaSuccess) ms = -1.0;
+    cudaFree(sink);
+    return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,217 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE: runs the kernels' __host__ __device__
+// phase functions (stark-anatomy_b200/csrc/*.cuh) on the CPU, thread by thread and
+// barrier phase by barrier phase, so the index maps, twiddle tables and the
+// portable field arithmetic can be checked against the oracle without a GPU.
+// It is NOT a fallback: nothing in the product loads this library.
+//
+// Build: g++ -O2 -std=c++17 -shared -fPIC -o libsa_emu.so emu.cpp
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../stark-anatomy_b200/csrc/field.cuh"
+#include "../../stark-anatomy_b200/csrc/fri_merkle.cuh"
+#include "../../stark-anatomy_b200/csrc/hash.cuh"
+#include "../../stark-anatomy_b200/csrc/ntt_plan.cuh"
+#include "../../stark-anatomy_b200/csrc/ntt_tile.cuh"
+
+using namespace sa;
+
+static fe from_limbs(const uint64_t x[2]) {
+    return fe_make((uint32_t)x[0], (uint32_t)(x[0] >> 32), (uint32_t)x[1], (uint32_t)(x[1] >> 32));
+}
+
+template <int LOGL>
+static void run_tiles(const TileArgs &a) {
+    using P = TilePlan<LOGL>;
+    const int tiles_per_batch = (a.ncols + TILE_C - 1) / TILE_C;
+    const long long total = (long long)tiles_per_batch * a.nbatch;
+    std::vector<fe> sm((size_t)P::L * TILE_C);
+    for (long long tile = 0; tile < total; tile++) {
+        const long long b = tile / tiles_per_batch;
+        const int col0 = (int)(tile % tiles_per_batch) * TILE_C;
+        // each loop over t is one barrier phase of the CTA
+        for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 0>(t, sm.data(), a, b, col0, true);
+        if constexpr (P::NST > 1)
+            for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 1>(t, sm.data(), a, b, col0, true);
+        if constexpr (P::NST > 2)
+            for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 2>(t, sm.data(), a, b, col0, true);
+    }
+}
+static void run_tiles_dyn(int logl, const TileArgs &a) {
+    switch (logl) {
+        case 1: run_tiles<1>(a); break;
+        case 2: run_tiles<2>(a); break;
+        case 3: run_tiles<3>(a); break;
+        case 4: run_tiles<4>(a); break;
+        case 5: run_tiles<5>(a); break;
+        case 6: run_tiles<6>(a); break;
+        case 7: run_tiles<7>(a); break;
+        case 8: run_tiles<8>(a); break;
+        case 9: run_tiles<9>(a); break;
+        case 10: run_tiles<10>(a); break;
+    }
+}
+static std::vector<fe> pow_table(const fe &base_m, const fe &lead_m, size_t count) {
+    std::vector<fe> t(count);
+    fe acc = lead_m;
+    for (size_t i = 0; i < count; i++) {
+        t[i] = acc;
+        acc = fe_montmul(acc, base_m);
+    }
+    return t;
+}
+
+extern "C" {
+
+void emu_montmul(uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    fe r = fe_montmul_portable(from_limbs(a), from_limbs(b));
+    memcpy(out, &r, 16);
+}
+void emu_mul(uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    fe r = fe_mul(from_limbs(a), from_limbs(b));
+    memcpy(out, &r, 16);
+}
+void emu_add(uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    fe r = fe_add_portable(from_limbs(a), from_limbs(b));
+    memcpy(out, &r, 16);
+}
+void emu_sub(uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    fe r = fe_sub_portable(from_limbs(a), from_limbs(b));
+    memcpy(out, &r, 16);
+}
+void emu_inv(uint64_t *out, const uint64_t *a) {
+    fe r = fe_from_mont(fe_mont_inv(fe_to_mont(from_limbs(a))));
+    memcpy(out, &r, 16);
+}
+
+// mirrors sa_ntt (sa_b200.cu): same plan, same tile passes
+int emu_ntt(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, int inverse, size_t batch) {
+    const size_t n = size_t(1) << log_n;
+    if (log_n == 0) {
+        memcpy(out, in, 16 * batch);
+        return 0;
+    }
+    const fe root_m = fe_to_mont(from_limbs(root));
+    if (!fe_eq(fe_mont_pow_u64(root_m, n), fe_mont_one())) return -2;
+    if (fe_eq(fe_mont_pow_u64(root_m, n / 2), fe_mont_one())) return -3;
+    const fe w_m = inverse ? fe_mont_inv(root_m) : root_m;
+    const fe ninv_m = fe_mont_inv(fe_to_mont(fe_from_u64(n)));
+    const NttShape s = ntt_shape(log_n);
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    fe cst1[8], cst2[8];
+    if (log_n <= 10) {
+        std::vector<fe> tw1 = pow_table(w_m, fe_mont_one(), n);
+        ntt_fill_cst(cst1, w_m, (int)n);
+        std::vector<fe> tmp((const fe *)in, (const fe *)in + n * batch);
+        ntt_fill_single(a, tmp.data(), (fe *)out, log_n, batch, tw1.data(), cst1, inverse ? 1 : 0,
+                        inverse ? ninv_m : fe_mont_one());
+        run_tiles_dyn(log_n, a);
+        return 0;
+    }
+    const size_t n1 = size_t(1) << s.l1, n2 = size_t(1) << s.l2;
+    const fe w1_m = fe_mont_pow_u64(w_m, n2), w2_m = fe_mont_pow_u64(w_m, n1);
+    std::vector<fe> tw1 = pow_table(w1_m, fe_mont_one(), n1), tw2 = pow_table(w2_m, fe_mont_one(), n2);
+    std::vector<fe> twb(n);
+    for (size_t k = 0; k < n1; k++) {
+        const fe wk = fe_mont_pow_u64(w_m, k);
+        fe acc = inverse ? ninv_m : fe_mont_one();
+        for (size_t j = 0; j < n2; j++) {
+            twb[k * n2 + j] = acc;
+            acc = fe_montmul(acc, wk);
+        }
+    }
+    ntt_fill_cst(cst1, w1_m, (int)n1);
+    ntt_fill_cst(cst2, w2_m, (int)n2);
+    std::vector<fe> tmp(n * batch);
+    ntt_fill_pass1(a, (const fe *)in, tmp.data(), s, batch, tw1.data(), twb.data(), cst1);
+    run_tiles_dyn(s.l1, a);
+    ntt_fill_pass2(a, tmp.data(), (fe *)out, s, batch, tw2.data(), cst2);
+    run_tiles_dyn(s.l2, a);
+    return 0;
+}
+
+uint32_t emu_decimal(uint8_t *buf40, const uint64_t *x) {
+    uint64_t w[5];
+    uint32_t n = fe_decimal_words(w, from_limbs(x));
+    memcpy(buf40, w, 40);
+    return n;
+}
+void emu_leaf_digest(uint8_t *out64, const uint64_t *x) {
+    uint64_t d[8];
+    merkle_leaf_digest(d, from_limbs(x));
+    memcpy(out64, d, 64);
+}
+void emu_node_digest(uint8_t *out64, const uint8_t *left, const uint8_t *right) {
+    uint64_t l[8], r[8], d[8];
+    memcpy(l, left, 64);
+    memcpy(r, right, 64);
+    merkle_node_digest(d, l, r);
+    memcpy(out64, d, 64);
+}
+
+// mirrors merkle_reduce / k_merkle_chunk (sa_b200.cu): chunked reduction, heap-ordered tree
+static void emu_merkle_reduce(MerkleArgs a) {
+    std::vector<uint64_t> sm((size_t)MK_CHUNK * 8);
+    while (true) {
+        a.chunk = (int)(a.width < MK_CHUNK ? a.width : MK_CHUNK);
+        const long long blocks = a.width / a.chunk;
+        for (long long blk = 0; blk < blocks; blk++) {
+            uint64_t d[8];
+            for (int tid = 0; tid < MK_THREADS; tid++)
+                for (int j = tid; j < a.chunk; j += MK_THREADS) {
+                    merkle_bottom(d, a, blk, j);
+                    for (int i = 0; i < 8; i++) sm[(size_t)j * 8 + i] = d[i];
+                }
+            long long gw = a.width / 2;
+            for (int wl = a.chunk / 2; wl >= 1; wl >>= 1, gw >>= 1) {
+                std::vector<uint64_t> regs((size_t)wl * 8);
+                for (int tid = 0; tid < wl; tid++)  // phase 1: read children, hash
+                    merkle_node_digest(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8],
+                                       &sm[(size_t)(2 * tid + 1) * 8]);
+                for (int tid = 0; tid < wl; tid++)  // phase 2: publish
+                    for (int i = 0; i < 8; i++) {
+                        sm[(size_t)tid * 8 + i] = regs[(size_t)tid * 8 + i];
+                        a.tree[(gw + blk * wl + tid) * 8 + i] = regs[(size_t)tid * 8 + i];
+                    }
+            }
+        }
+        if (a.width <= MK_CHUNK) break;
+        a.width /= MK_CHUNK;
+        a.mode = 0;
+    }
+}
+int emu_merkle_tree(uint8_t *tree, const uint64_t *values, size_t n) {
+    memset(tree, 0, 64);
+    MerkleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = (uint64_t *)tree;
+    a.width = (long long)n;
+    a.mode = 1;
+    a.values = (const fe *)values;
+    emu_merkle_reduce(a);
+    return 0;
+}
+int emu_fri_round(uint64_t *next, uint8_t *next_tree, const uint64_t *cw, size_t n, const uint64_t *alpha,
+                  const uint64_t *offset, const uint64_t *omega) {
+    memset(next_tree, 0, 64);
+    const fe winv_m = fe_mont_inv(fe_to_mont(from_limbs(omega)));
+    std::vector<fe> xinv = pow_table(winv_m, fe_mont_one(), n / 2);
+    MerkleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = (uint64_t *)next_tree;
+    a.width = (long long)(n / 2);
+    a.mode = 2;
+    a.prev = (const fe *)cw;
+    a.next = (fe *)next;
+    a.xinv = xinv.data();
+    a.inv2_m = fe_mont_inv(fe_to_mont(fe_from_u64(2)));
+    const fe oinv_m = fe_mont_inv(fe_to_mont(from_limbs(offset)));
+    a.s_m = fe_montmul(fe_montmul(fe_to_mont(from_limbs(alpha)), a.inv2_m), oinv_m);
+    emu_merkle_reduce(a);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""Pin the CPU oracle (oracle/) to the reference's own outputs.
+
+Every check compares the C / Python restatement against tests/golden/*.json,
+which tests/golden/make_golden.py produced by importing the unmodified Python
+reference, or against the 2^20 digests recorded in BASELINE.md section 3.
+"""
+import hashlib
+import pickle
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import ints, load_golden
+
+P = O.P
+
+
+def test_field_ops():
+    g = load_golden("field.json")
+    assert int(g["p"]) == P and int(g["generator"]) == O.GENERATOR
+    L = O.lib()
+    out = np.zeros(2, dtype=np.uint64)
+
+    def call(fn, *args):
+        fn(O._ptr(out), *[O._ptr(O._fe(a)) for a in args])
+        return int(out[0]) | (int(out[1]) << 64)
+    for c in g["cases"]:
+        a, b = int(c["a"]), int(c["b"])
+        assert call(L.so_fe_add, a, b) == int(c["add"])
+        assert call(L.so_fe_sub, a, b) == int(c["sub"])
+        assert call(L.so_fe_mul, a, b) == int(c["mul"])
+        assert call(L.so_fe_inv, a) == int(c["inv"]) == O.inverse(a)
+        assert call(L.so_fe_pow, a, b % 1000003) == int(c["pow"])
+    for n, r in g["roots"].items():
+        assert O.primitive_nth_root(int(n)) == int(r)
+    for s in g["samples"]:
+        assert O.sample(bytes.fromhex(s["bytes"])) == int(s["value"])
+    for b in g["bytes"]:
+        assert O.decimal(int(b["v"])) == b["s"].encode()
+
+
+def test_ntt_golden_vectors():
+    g = load_golden("ntt.json")
+    for c in g["ntt"]:
+        root, xs, ys = int(c["root"]), ints(c["in"]), ints(c["out"])
+        assert O.ntt(root, xs) == ys, f"ntt n={c['n']} seed={c['seed']}"
+        if c["n"] <= 64:
+            assert O.py_ntt(root, xs) == ys
+    for c in g["intt"]:
+        assert O.intt(int(c["root"]), ints(c["in"])) == ints(c["out"]), f"intt n={c['n']}"
+
+
+def test_ntt_parallel_equals_serial():
+    rng = random.Random(7)
+    n = 1 << 15
+    a = O.to_np([rng.randrange(P) for _ in range(n)])
+    w = O.primitive_nth_root(n)
+    assert (O.ntt_np(w, a) == O.ntt_np(w, a, parallel=True)).all()
+    b = np.stack([a, a[::-1].copy()])
+    got = O.ntt_batch_np(w, b)
+    assert (got[0] == O.ntt_np(w, a)).all() and (got[1] == O.ntt_np(w, b[1])).all()
+
+
+def test_ntt_asserts():
+    with pytest.raises(AssertionError, match="non-power-of-two"):
+        O.ntt(O.primitive_nth_root(4), [1, 2, 3])
+    with pytest.raises(AssertionError, match="must be nth root"):
+        O.ntt(O.primitive_nth_root(8), [1, 2, 3, 4])
+    with pytest.raises(AssertionError, match="not primitive"):
+        O.ntt(O.primitive_nth_root(2), [1, 2, 3, 4])
+
+
+def _seeded(seed, n):
+    rng = random.Random(seed)
+    return O.to_np([rng.randrange(P) for _ in range(n)])
+
+
+def test_ntt_digests_mid():
+    g = load_golden("ntt.json")
+    for c in g["digests"]:
+        if c["n"] > 1 << 14:
+            continue
+        a = _seeded(c["seed"], c["n"])
+        assert O.vector_digest(O.ntt_np(int(c["root"]), a)) == c["ntt"]
+        assert O.vector_digest(O.intt_np(int(c["root"]), a)) == c["intt"]
+
+
+@pytest.mark.slow
+def test_ntt_digest_2_20_baseline():
+    """2^20 ntt output digest (189.7 s of reference time)."""
+    c = [c for c in load_golden("ntt.json")["digests"] if c["n"] == 1 << 20][0]
+    a = _seeded(0, 1 << 20)
+    y = O.ntt_np(int(c["root"]), a, parallel=True)
+    assert O.vector_digest(y) == c["ntt"]
+    assert (O.intt_np(int(c["root"]), y, parallel=True) == a).all()
+
+
+def test_poly_golden():
+    g = load_golden("poly.json")
+    for c in g["multiply"]:
+        got = O.fast_multiply(ints(c["lhs"]), ints(c["rhs"]), int(c["root"]), c["order"])
+        assert got == ints(c["out"])
+    for c in g["coset_evaluate"]:
+        got = O.fast_coset_evaluate(ints(c["coeffs"]), int(c["offset"]), int(c["generator"]), c["order"])
+        assert got == ints(c["out"])
+    for c in g["coset_divide"]:
+        lhs, rhs = ints(c["lhs"]), ints(c["rhs"])
+        if max(O.degree(lhs), O.degree(rhs)) < 8 and lhs:
+            continue  # ntt.py:152-153 long-division fallback: host Polynomial code, not oracle scope
+        got = O.fast_coset_divide(lhs, rhs, int(c["offset"]), int(c["root"]), c["order"])
+        assert got == ints(c["out"])
+    for c in g["evaluate"]:
+        coeffs, dom = ints(c["coeffs"]), ints(c["domain"])
+        if not dom:
+            continue
+        got = O.from_np(O.poly_eval_np(O.to_np(coeffs), O.to_np(dom)))
+        assert got == ints(c["out"])
+    for c in g["zerofier"]:
+        dom, zf = ints(c["domain"]), ints(c["out"])
+        if dom:
+            assert len(zf) == len(dom) + 1 and zf[-1] == 1
+            assert O.from_np(O.poly_eval_np(O.to_np(zf), O.to_np(dom))) == [0] * len(dom)
+    for c in g["interpolate"]:
+        dom, vals, poly = ints(c["domain"]), ints(c["values"]), ints(c["out"])
+        if dom:
+            assert len(poly) == len(dom)
+            assert O.from_np(O.poly_eval_np(O.to_np(poly), O.to_np(dom))) == vals
+
+
+@pytest.mark.slow
+def test_fast_multiply_digests():
+    for c in load_golden("poly.json")["big"]:
+        n = c["n"]
+        rng = random.Random(c["seed"])
+        lhs = [rng.randrange(P) for _ in range(n // 2)]
+        rhs = [rng.randrange(P) for _ in range(n // 2)]
+        got = O.fast_multiply(lhs, rhs, O.primitive_nth_root(n), n)
+        assert len(got) == n - 1
+        assert O.vector_digest(O.to_np(got)) == c["digest"]
+
+
+def test_blake2b_matches_hashlib():
+    rng = random.Random(11)
+    for n in list(range(0, 70)) + [127, 128, 129, 255, 256, 257, 1000]:
+        msg = bytes(rng.randrange(256) for _ in range(n))
+        assert O.blake2b(msg) == hashlib.blake2b(msg).digest()
+
+
+def test_merkle_golden():
+    g = load_golden("merkle.json")
+    for c in g["leaf"]:
+        assert O.blake2b(O.decimal(int(c["v"]))).hex() == c["digest"]
+    trees = {}
+    for c in g["commit"]:
+        if "in" in c:
+            arr = O.to_np(ints(c["in"]))
+        elif c["n"] <= 1 << 14:
+            arr = _seeded(c["seed"], c["n"])
+        else:
+            continue
+        tree = O.merkle_tree_np(arr)
+        trees[(c["seed"], c["n"])] = tree
+        assert tree[1].tobytes().hex() == c["root"]
+    for c in g["open"]:
+        tree = trees[(c["seed"], c["n"])]
+        assert [p.hex() for p in O.merkle_open(tree, c["index"])] == c["path"]
+
+
+def test_fri_fold_golden():
+    for c in load_golden("fri.json")["fold"]:
+        got = O.fri_fold_np(O.to_np(ints(c["in"])), int(c["alpha"]), int(c["offset"]), int(c["omega"]))
+        assert O.from_np(got) == ints(c["out"])
+
+
+def test_fri_commit_golden():
+    for c in load_golden("fri.json")["commit"]:
+        if c["n"] > 1 << 14:
+            continue
+        n = c["n"]
+        cw = _seeded(c["seed"], n)
+        roots, alphas, layers = O.fri_commit_np(cw, O.GENERATOR, O.primitive_nth_root(n), c["ef"], c["tests"])
+        assert len(roots) == c["rounds"] == O.fri_num_rounds(n, c["ef"], c["tests"])
+        assert [r.hex() for r in roots] == c["roots"]
+        assert [l.shape[0] for l in layers] == c["layer_lens"]
+        assert [O.vector_digest(l) for l in layers] == c["layer_digests"]
+        assert O.from_np(layers[-1]) == ints(c["last"])
+
+
+@pytest.mark.slow
+def test_fri_commit_2_20_baseline():
+    """12 FRI round roots at N = 2^20 (73.1 s of reference time)."""
+    c = [c for c in load_golden("fri.json")["commit"] if c["n"] == 1 << 20][0]
+    n = 1 << 20
+    roots, alphas, layers = O.fri_commit_np(_seeded(1, n), O.GENERATOR, O.primitive_nth_root(n), 4, 64)
+    assert [r[:8].hex() for r in roots] == c["roots8"]
+    m = [m for m in load_golden("merkle.json")["commit"] if m["n"] == 1 << 20][0]
+    assert roots[0].hex() == m["root"]
+
+
+def test_sample_indices_matches_prove_fixture():
+    """fri.py:36-51 restated; checked through the indices Fri.prove returned."""
+    from hostmirror_loader import load_host_types
+    T = load_host_types()
+    for c in load_golden("fri.json")["prove"]:
+        if "objects" not in c:
+            continue
+        objs = [T.dec_obj(o) for o in c["objects"]]
+        assert hashlib.sha256(pickle.dumps(objs)).hexdigest() == c["transcript_sha256"]
+        # commit-phase objects = everything up to and including the last codeword (a list)
+        k = max(i for i, o in enumerate(objs) if isinstance(o, list) and o and not isinstance(o[0], bytes))
+        seed = hashlib.shake_256(pickle.dumps(objs[:k + 1])).digest(32)
+        rounds = O.fri_num_rounds(c["n"], c["ef"], c["tests"])
+        got = O.sample_indices(seed, c["n"] // 2, c["n"] >> (rounds - 1), c["tests"])
+        assert got == c["indices"]
