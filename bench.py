@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 NTT + FRI engine (contract: task prompt section 4).
+
+Metric (BASELINE.json): 128-bit field butterflies/sec on 2^20-point NTTs; FRI commit ms @ 2^20.
+One "step" = one pass of the hot path over one batch: BATCH independent 2^20-point forward
+NTTs (code/ntt.py:3-18) resident in HBM (BATCH * 16 MiB = 256 MiB > the 126 MB L2, so every
+step streams from HBM).  butterflies := (n/2) * log2 n per transform.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+N > 1: one process per GPU, every rank transforms its own batch (weak scaling, no data-path
+collective); time is the max over ranks.  --impl reference times the CPU oracle port
+(oracle/stark_oracle.c, all host threads) on the same workload definition.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "stark-anatomy_b200"), os.path.join(ROOT, "oracle"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+LOG_N = 20
+N = 1 << LOG_N
+BATCH = 16
+BUTTERFLIES_PER_NTT = (N // 2) * LOG_N  # 10 485 760
+METRIC = "128-bit field butterflies/sec on 2^20 NTT"
+UNIT = "butterflies/s"
+WORKLOAD = "batch of %d independent 2^20-point forward NTTs over p=1+407*2^119 (configs[1] size, batched)" % BATCH
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(steps, warmup, batch):
+    """the CPU oracle port on all host threads; returns (butterflies/s, threads, seconds/step)"""
+    import numpy as np
+    import oracle as O
+    rng = np.random.default_rng(0)
+    x = np.stack([rng.integers(0, 1 << 64, size=(batch, N), dtype=np.uint64),
+                  rng.integers(0, 0xCB80000000000000, size=(batch, N), dtype=np.uint64)], axis=2)
+    w = O.primitive_nth_root(N)
+    threads = O.lib().so_num_threads()
+    for _ in range(warmup):
+        O.ntt_batch_np(w, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.ntt_batch_np(w, x)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch * BUTTERFLIES_PER_NTT / dt, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as G
+    G.build_oracle()
+    value, threads, dt = cpu_arm(args.steps, args.warmup, BATCH)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u128 mod p (CPU unsigned __int128)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "log_n": LOG_N, "batch": BATCH},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d steps of %d x 2^20-point ntt, oracle/stark_oracle.c so_ntt_batch (OpenMP, one "
+                                   "transform per thread); the reference itself is single-threaded pure Python "
+                                   "(5.5e4 butterflies/s, BASELINE.md section 2)" % (args.steps, BATCH)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import __graft_entry__ as G
+    G._paths()
+    import sa_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = sa_engine.get_engine()
+    lib = eng.lib
+    dev = eng.device
+    peak, peak_src = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs resident in HBM: BATCH * 16 MiB, canonical residues, per-rank seed
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    lo = torch.randint(-(1 << 63), (1 << 63) - 1, (BATCH * N,), dtype=torch.int64, device=dev, generator=g)
+    hi = torch.randint(0, 0x4B80000000000000, (BATCH * N,), dtype=torch.int64, device=dev, generator=g)
+    x = torch.stack([lo, hi], dim=1).contiguous()  # hi limb < 2^63 < p's top limb: canonical
+    y = torch.empty_like(x)
+    import oracle as O
+    w = O.primitive_nth_root(N)
+    root = sa_engine._limbs(w)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        rc = lib.sa_ntt(y.data_ptr(), x.data_ptr(), LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError("sa_ntt failed: %d %s" % (rc, lib.sa_last_error().decode()))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # spot parity check inside the bench: transform 0 of this rank against the oracle
+    if rank == 0:
+        want = O.ntt_np(w, x[:N].cpu().numpy().view(np.uint64), parallel=True)
+        assert (y[:N].cpu().numpy().view(np.uint64) == want).all(), "bench output differs from the oracle"
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.sa_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.sa_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * BATCH * BUTTERFLIES_PER_NTT * args.steps / (ms * 1e-3)
+
+    # ---- single-transform latency (device resident), for the record
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    ev2.record(stream)
+    for i in range(reps):
+        off = (i % BATCH) * N
+        lib.sa_ntt(y[off:off + N].data_ptr(), x[off:off + N].data_ptr(), LOG_N, root, 0, 1,
+                   ctypes.c_void_p(stream.cuda_stream))
+    ev3.record(stream)
+    torch.cuda.synchronize()
+    single_us = ev2.elapsed_time(ev3) / reps * 1e3
+
+    # ---- e2e: the same step through the C-ABI host entry (pinned host buffers, H2D + D2H inside)
+    hx = torch.empty_like(x, device="cpu").pin_memory()
+    hy = torch.empty_like(x, device="cpu").pin_memory()
+    hx.copy_(x)
+    e2e_steps = max(2, min(args.steps, 5))
+    lib.sa_ntt_host(hy.data_ptr(), hx.data_ptr(), LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = lib.sa_ntt_host(hy.data_ptr(), hx.data_ptr(), LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
+        assert rc == 0
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * BATCH * BUTTERFLIES_PER_NTT / float(e2e_s.item())
+    if rank == 0:
+        assert (hy[:N].numpy().view(np.uint64) == want).all(), "e2e output differs from the oracle"
+
+    # ---- FRI commit ms @ 2^20 (second half of BASELINE.json's metric), rank 0 only, list API excluded:
+    #      device-resident codeword, 12 fused rounds, host Fiat-Shamir on the 64-byte roots
+    fri_ms = fri_cpu_ms = None
+    if rank == 0:
+        import hashlib
+        import pickle
+        cw = x[:N]
+        omega0, off0 = w, O.GENERATOR
+        rounds = O.fri_num_rounds(N, 4, 64)
+
+        def fri_commit():
+            objs, vec = [], cw
+            omega, off = omega0, off0
+            tree = eng.merkle_tree(vec)
+            for r in range(rounds):
+                objs.append(eng.tree_root(tree))
+                if r == rounds - 1:
+                    break
+                alpha = O.sample(hashlib.shake_256(pickle.dumps(objs)).digest(32))
+                vec, tree = eng.fri_round(vec, alpha, off, omega)
+                omega, off = omega * omega % O.P, off * off % O.P
+            return objs
+        fri_commit()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            roots = fri_commit()
+        torch.cuda.synchronize()
+        fri_ms = (time.perf_counter() - t0) / 3 * 1e3
+        t0 = time.perf_counter()
+        oroots, _, _ = O.fri_commit_np(cw.cpu().numpy().view(np.uint64), off0, omega0, 4, 64)
+        fri_cpu_ms = (time.perf_counter() - t0) * 1e3
+        assert roots == oroots, "FRI commit roots differ from the oracle"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores, bounded sample (~10-20 s)
+    cpu_value, cpu_threads, cpu_dt = cpu_arm(2, 1, BATCH)
+
+    # roofline of the dominant kernel, ntt_tile_kernel<10>: two launches per step (column pass, row pass);
+    # each launch reads and writes the whole batch once: 32 * n * BATCH algorithmic bytes
+    launches_per_step = 2
+    alg_bytes_per_launch = 32 * N * BATCH
+    launch_s = ms_per_step * 1e-3 / launches_per_step
+    achieved = alg_bytes_per_launch / launch_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u128 mod p (4x u32 limbs, Montgomery)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "log_n": LOG_N, "batch_per_gpu": BATCH,
+                   "l2": "inputs larger than L2: %d MiB in + %d MiB out per step" % (BATCH * 16, BATCH * 16),
+                   "parallelism": "batch sharded across %d GPU(s), no collective in the timed region" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "ntt_tile_kernel<10>", "launches_per_step": launches_per_step,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
+                     "note": "integer-issue bound expected to bind first (SURVEY.md 8d); see profiles/"},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP); reference "
+                                   "pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * 16,
+                "d2h_bytes_per_step": BATCH * N * 16, "api": "sa_ntt_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "single_ntt_us": single_us,
+        "fri_commit_ms_2_20": fri_ms, "fri_commit_cpu_port_ms_2_20": fri_cpu_ms,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,326 @@
+"""Drop-in for the reference's code/fri.py, backed by the B200 engine.
+
+``from fri import *`` (code/fast_stark.py:1) resolves here when this directory is
+ahead of the reference's on sys.path.  It re-exports the names the reference's
+fri module exports (algebra, merkle, ip, ntt, univariate names, hexlify,
+unhexlify, math, blake2b) and provides ``Fri`` with the reference's constructor,
+``num_rounds``, ``sample_index(es)``, ``eval_domain``, ``commit``, ``query``,
+``prove`` and ``verify``.
+
+Device flow of ``commit`` (code/fri.py:56-96): the codeword is uploaded once; the
+Merkle tree of round 0 is built on the GPU; every later round is ONE fused
+kernel (fold + leaf hashing + subtree reduction, ``sa_fri_round``).  Per round a
+64-byte root comes back to the host because the challenge is
+``field.sample(proof_stream.prover_fiat_shamir())`` on the caller's proof stream
+object (possibly a subclass, code/fast_rpsss.py:7-17).  Trees stay on the device
+for ``query`` (code/fri.py:98-113), which gathers leaf triples and
+authentication paths instead of re-hashing whole layers per opened index.
+
+Pushed objects have the reference's types and object identity structure (root
+``bytes``, the last codeword as a ``list`` of ``algebra.FieldElement``, tuples of
+the SAME element objects a layer list would hold, ``list[bytes]`` paths), so
+``pickle.dumps(proof_stream.objects)`` is byte-identical to the reference's.
+"""
+import sa_host  # noqa: F401
+from algebra import *  # noqa: F401,F403
+from merkle import *  # noqa: F401,F403
+from ip import *  # noqa: F401,F403
+from ntt import *  # noqa: F401,F403
+from binascii import hexlify, unhexlify  # noqa: F401
+import math  # noqa: F401
+from hashlib import blake2b
+
+from univariate import *  # noqa: F401,F403
+from univariate import Polynomial, test_colinearity
+from algebra import FieldElement
+from merkle import Merkle
+from ntt import intt
+
+import sa_engine
+import sa_marshal
+
+
+class DeviceCodeword:
+    """A FRI layer that lives on the GPU and behaves like the list the reference
+    returns from ``Fri.commit``: len(), indexing, iteration, ==.  Elements are
+    materialised on demand and cached, so repeated indexing returns the SAME
+    FieldElement object (a real list would, and pickle's memo sees the difference).
+    """
+
+    def __init__(self, vec, tree, field, length):
+        self._vec, self._tree, self._field, self._len = vec, tree, field, length
+        self._cache = {}
+        self._full = None
+
+    def __len__(self):
+        return self._len
+
+    def prefetch(self, indices):
+        missing = [i for i in dict.fromkeys(indices) if i not in self._cache]
+        if self._full is not None or not missing:
+            return
+        raw = sa_engine.get_engine().gather(self._vec, missing)
+        for i, el in zip(missing, sa_marshal.unpack(raw, self._field, FieldElement)):
+            self._cache[i] = el
+
+    def tolist(self):
+        if self._full is None:
+            full = sa_marshal.unpack(sa_engine.get_engine().download(self._vec), self._field, FieldElement)
+            for i, el in self._cache.items():  # keep identities handed out earlier
+                full[i] = el
+            self._full = full
+        return self._full
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self.tolist()[i]
+        if i < 0:
+            i += self._len
+        if not 0 <= i < self._len:
+            raise IndexError("list index out of range")
+        if self._full is not None:
+            return self._full[i]
+        if i not in self._cache:
+            self.prefetch([i])
+        return self._cache[i]
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __eq__(self, other):
+        return self.tolist() == (other.tolist() if isinstance(other, DeviceCodeword) else other)
+
+    __hash__ = None
+
+
+class Fri:
+    def __init__(self, offset, omega, initial_domain_length, expansion_factor, num_colinearity_tests):
+        self.offset = offset
+        self.omega = omega
+        self.domain_length = initial_domain_length
+        self.field = omega.field
+        self.expansion_factor = expansion_factor
+        self.num_colinearity_tests = num_colinearity_tests
+        self._resident = {}  # id(list) -> (list, device vector, device tree) of the last commit
+        assert(self.num_rounds() >= 1), "cannot do FRI with less than one round"
+
+    # ------------------------------------------------------- host helpers --
+    def num_rounds(self):
+        """code/fri.py:22-28"""
+        codeword_length = self.domain_length
+        num_rounds = 0
+        while codeword_length > self.expansion_factor and 4 * self.num_colinearity_tests < codeword_length:
+            codeword_length /= 2
+            num_rounds += 1
+        return num_rounds
+
+    def sample_index(byte_array, size):
+        """code/fri.py:30-34: big-endian integer of the bytes, reduced mod size"""
+        return int.from_bytes(bytes(byte_array), "big") % size
+
+    def sample_indices(self, seed, size, reduced_size, number):
+        """code/fri.py:36-51 (bytes(counter) is `counter` zero bytes, as in the reference)"""
+        assert(number <= reduced_size), f"cannot sample more indices than available in last codeword; requested: {number}, available: {reduced_size}"
+        assert(number <= 2 * reduced_size), "not enough entropy in indices wrt last codeword"
+        indices, reduced_indices = [], []
+        counter = 0
+        while len(indices) < number:
+            index = Fri.sample_index(blake2b(seed + bytes(counter)).digest(), size)
+            reduced_index = index % reduced_size
+            counter += 1
+            if reduced_index not in reduced_indices:
+                indices += [index]
+                reduced_indices += [reduced_index]
+        return indices
+
+    def eval_domain(self):
+        return [self.offset * (self.omega ^ i) for i in range(self.domain_length)]
+
+    # --------------------------------------------------------------- commit --
+    def commit(self, codeword, proof_stream, round_index=0):
+        eng = sa_engine.get_engine()
+        p = self.field.p
+        omega, offset = self.omega.value, self.offset.value
+        codewords = []
+        self._resident = {}
+        rounds = self.num_rounds()
+
+        current = codeword  # what the reference would hold in `codeword`
+        vec = eng.upload(sa_marshal.pack(codeword))
+        tree = eng.merkle_tree(vec)  # round 0: leaf hashing + tree, no fold
+
+        for r in range(rounds):
+            N = len(current)
+            # make sure omega has the right order
+            assert(pow(omega, N - 1, p) == pow(omega, -1, p)), "error in commit: omega does not have the right order!"
+            # compute and send Merkle root
+            proof_stream.push(eng.tree_root(tree))
+            # prepare next round, but only if necessary
+            if r == rounds - 1:
+                break
+            # get challenge
+            alpha = self.field.sample(proof_stream.prover_fiat_shamir())
+            # collect codeword
+            codewords += [current]
+            if not isinstance(current, DeviceCodeword):
+                self._resident[id(current)] = (current, vec, tree)
+            # split and fold (fri.py:85) fused with the next round's leaf hashing and tree
+            vec, tree = eng.fri_round(vec, alpha.value, offset, omega)
+            current = DeviceCodeword(vec, tree, self.field, N // 2)
+            omega = omega * omega % p
+            offset = offset * offset % p
+
+        # send last codeword (a real list: it is pickled into the transcript)
+        last = current if not isinstance(current, DeviceCodeword) else current.tolist()
+        proof_stream.push(last)
+        self._resident[id(last)] = (last, vec, tree)
+        # collect last codeword too
+        codewords = codewords + [last]
+        return codewords
+
+    # ---------------------------------------------------------------- query --
+    def _device_layer(self, layer):
+        """(vector, tree) of a layer: resident from commit, else uploaded and hashed now"""
+        if isinstance(layer, DeviceCodeword):
+            return layer._vec, layer._tree
+        hit = self._resident.get(id(layer))
+        if hit is not None and hit[0] is layer:
+            return hit[1], hit[2]
+        eng = sa_engine.get_engine()
+        vec = eng.upload(sa_marshal.pack(layer))
+        tree = eng.merkle_tree(vec)
+        self._resident[id(layer)] = (layer, vec, tree)
+        return vec, tree
+
+    def query(self, current_codeword, next_codeword, c_indices, proof_stream):
+        eng = sa_engine.get_engine()
+        # infer a and b indices
+        a_indices = [index for index in c_indices]
+        b_indices = [index + len(current_codeword) // 2 for index in c_indices]
+        s_range = range(self.num_colinearity_tests)
+
+        if isinstance(current_codeword, DeviceCodeword):
+            current_codeword.prefetch([a_indices[s] for s in s_range] + [b_indices[s] for s in s_range])
+        if isinstance(next_codeword, DeviceCodeword):
+            next_codeword.prefetch([c_indices[s] for s in s_range])
+
+        # reveal leafs
+        for s in s_range:
+            proof_stream.push((current_codeword[a_indices[s]], current_codeword[b_indices[s]], next_codeword[c_indices[s]]))
+
+        # reveal authentication paths: one gather per layer from the resident trees
+        _, cur_tree = self._device_layer(current_codeword)
+        _, nxt_tree = self._device_layer(next_codeword)
+        cur_paths = eng.merkle_open(cur_tree, [a_indices[s] for s in s_range] + [b_indices[s] for s in s_range])
+        nxt_paths = eng.merkle_open(nxt_tree, [c_indices[s] for s in s_range])
+        k = self.num_colinearity_tests
+        for s in s_range:
+            proof_stream.push(cur_paths[s])
+            proof_stream.push(cur_paths[k + s])
+            proof_stream.push(nxt_paths[s])
+
+        return a_indices + b_indices
+
+    # ---------------------------------------------------------------- prove --
+    def prove(self, codeword, proof_stream):
+        assert(self.domain_length == len(codeword)), "initial codeword length does not match length of initial codeword"
+
+        # commit phase
+        codewords = self.commit(codeword, proof_stream)
+
+        # get indices
+        top_level_indices = self.sample_indices(proof_stream.prover_fiat_shamir(), len(codewords[0]) // 2, len(codewords[-1]), self.num_colinearity_tests)
+        indices = [index for index in top_level_indices]
+
+        # query phase
+        for i in range(len(codewords) - 1):
+            indices = [index % (len(codewords[i]) // 2) for index in indices]  # fold
+            self.query(codewords[i], codewords[i + 1], indices, proof_stream)
+
+        return top_level_indices
+
+    # --------------------------------------------------------------- verify --
+    def verify(self, proof_stream, polynomial_values):
+        """Verifier (code/fri.py:132-231).  Same accept/reject decisions and the same
+        pulls from the proof stream; the low-degree check of the last codeword uses
+        the inverse transform the tutorial text describes (docs/faster.md, commented
+        out at code/fri.py:165-166) instead of cubic-time Lagrange interpolation."""
+        eng = sa_engine.get_engine()
+        p = self.field.p
+        rounds = self.num_rounds()
+
+        # extract all roots and alphas
+        roots, alphas = [], []
+        for r in range(rounds):
+            roots += [proof_stream.pull()]
+            alphas += [self.field.sample(proof_stream.verifier_fiat_shamir())]
+
+        # extract last codeword and check it against the last root
+        last_codeword = proof_stream.pull()
+        last_vec = eng.upload(sa_marshal.pack(last_codeword))
+        if roots[-1] != eng.tree_root(eng.merkle_tree(last_vec)):
+            print("last codeword is not well formed")
+            return False
+
+        # check if it is low degree
+        degree = (len(last_codeword) // self.expansion_factor) - 1
+        last_omega = FieldElement(pow(self.omega.value, 1 << (rounds - 1), p), self.field)
+        last_offset = FieldElement(pow(self.offset.value, 1 << (rounds - 1), p), self.field)
+        assert(last_omega.inverse() == last_omega ^ (len(last_codeword) - 1)), "omega does not have right order"
+        coefficients = intt(last_omega, last_codeword)
+        poly = Polynomial(coefficients).scale(last_offset.inverse())
+        if poly.degree() > degree:
+            print("last codeword does not correspond to polynomial of low enough degree")
+            print("observed degree:", poly.degree())
+            print("but should be:", degree)
+            return False
+
+        # get indices
+        top_level_indices = self.sample_indices(proof_stream.verifier_fiat_shamir(), self.domain_length >> 1, self.domain_length >> (rounds - 1), self.num_colinearity_tests)
+
+        omega, offset = self.omega, self.offset
+        # for every round, check consistency of subsequent layers
+        for r in range(0, rounds - 1):
+            half = self.domain_length >> (r + 1)
+            c_indices = [index % half for index in top_level_indices]
+            a_indices = [index for index in c_indices]
+            b_indices = [index + half for index in a_indices]
+
+            # read values and check colinearity
+            aa, bb, cc = [], [], []
+            for s in range(self.num_colinearity_tests):
+                (ay, by, cy) = proof_stream.pull()
+                aa += [ay]
+                bb += [by]
+                cc += [cy]
+                # record top-layer values for later verification
+                if r == 0:
+                    polynomial_values += [(a_indices[s], ay), (b_indices[s], by)]
+                ax = offset * (omega ^ a_indices[s])
+                bx = offset * (omega ^ b_indices[s])
+                cx = alphas[r]
+                if test_colinearity([(ax, ay), (bx, by), (cx, cy)]) == False:  # noqa: E712
+                    print("colinearity check failure")
+                    return False
+
+            # verify authentication paths
+            for i in range(self.num_colinearity_tests):
+                path = proof_stream.pull()
+                if Merkle.verify(roots[r], a_indices[i], path, aa[i]) == False:  # noqa: E712
+                    print("merkle authentication path verification fails for aa")
+                    return False
+                path = proof_stream.pull()
+                if Merkle.verify(roots[r], b_indices[i], path, bb[i]) == False:  # noqa: E712
+                    print("merkle authentication path verification fails for bb")
+                    return False
+                path = proof_stream.pull()
+                if Merkle.verify(roots[r + 1], c_indices[i], path, cc[i]) == False:  # noqa: E712
+                    print("merkle authentication path verification fails for cc")
+                    return False
+
+            # square omega and offset to prepare for next round
+            omega = omega ^ 2
+            offset = offset ^ 2
+
+        # all checks passed
+        return True

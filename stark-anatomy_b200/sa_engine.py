@@ -1,0 +1,255 @@
+"""sa_engine -- ctypes binding of the C ABI (include/sa_b200.h) plus device memory.
+
+This is the "reference-side binding a maintainer would add" (INTEGRATION.md):
+plain pointers and sizes go to ``libsa_b200.so``; PyTorch is used only for
+device memory (``torch.empty(..., device="cuda")``), host<->device copies and the
+current CUDA stream.  There is no CPU fallback: creating the engine without a
+CUDA device or without the built library raises.
+
+Vectors are ``torch.int64`` tensors of shape [n, 2] on the GPU holding the
+(lo, hi) limbs of canonical residues mod p = 1 + 407*2^119 (16 bytes/element).
+"""
+import ctypes
+import os
+
+P = 1 + 407 * (1 << 119)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsa_b200.so")
+
+# include/sa_b200.h error codes -> the reference's assertion messages
+SA_ERRORS = {
+    -1: "cannot compute ntt of non-power-of-two sequence",                                   # ntt.py:4
+    -2: "primitive root must be nth root of unity, where n is len(values)",                  # ntt.py:10
+    -3: "primitive root is not primitive nth root of unity, where n is len(values)",         # ntt.py:11
+    -4: "divide by zero",                                                                    # algebra.py:92
+    -5: "cannot open invalid index",                                                         # merkle.py:18
+    -6: "unsupported size",
+}
+
+# every symbol include/sa_b200.h declares: (name, restype, argtypes)
+_vp, _sz, _ci, _u64p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)
+SYMBOLS = [
+    ("sa_version", ctypes.c_char_p, []),
+    ("sa_last_error", ctypes.c_char_p, []),
+    ("sa_launch_count", ctypes.c_uint64, []),
+    ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_pointwise_mul", _ci, [_vp, _vp, _vp, _sz, _vp]),
+    ("sa_pointwise_div", _ci, [_vp, _vp, _vp, _sz, _vp]),
+    ("sa_scale", _ci, [_vp, _vp, _sz, _u64p, _vp]),
+    ("sa_poly_eval", _ci, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    ("sa_merkle_tree", _ci, [_vp, _vp, _sz, _vp]),
+    ("sa_merkle_open", _ci, [_vp, _vp, _sz, _u64p, _sz, _vp]),
+    ("sa_gather", _ci, [_vp, _vp, _sz, _u64p, _sz, _vp]),
+    ("sa_fri_fold", _ci, [_vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
+    ("sa_fri_round", _ci, [_vp, _vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
+    ("sa_selftest_field", ctypes.c_longlong, [_sz, ctypes.c_uint64]),
+    ("sa_microbench", ctypes.c_double, [_ci, _ci, _ci, _ci, _ci]),
+]
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the C-ABI library and type every entry point (works without a GPU)."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "stark-anatomy_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+def _limbs(x):
+    x = int(x)
+    return (ctypes.c_uint64 * 2)(x & 0xFFFFFFFFFFFFFFFF, x >> 64)
+
+
+class SaError(AssertionError):
+    """Raised with the reference's assertion message for SA_E* codes."""
+
+
+class CudaEngine:
+    """Device-resident operations; one instance per process (one process per GPU)."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("stark-anatomy_b200: no CUDA device visible; the engine has no CPU fallback")
+        self.torch = torch
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+    # ------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        if rc in SA_ERRORS:
+            raise SaError(SA_ERRORS[rc])
+        raise RuntimeError("sa_b200: CUDA error: %s" % self.lib.sa_last_error().decode())
+
+    def empty(self, n):
+        return self.torch.empty((n, 2), dtype=self.torch.int64, device=self.device)
+
+    def zeros(self, n):
+        return self.torch.zeros((n, 2), dtype=self.torch.int64, device=self.device)
+
+    def length(self, vec):
+        return vec.shape[0]
+
+    def upload(self, buf):
+        """packed 16-byte elements (bytearray / numpy / pinned tensor) -> device vector"""
+        torch = self.torch
+        if isinstance(buf, torch.Tensor):
+            return buf.reshape(-1, 2).to(self.device, non_blocking=True)
+        if len(buf) == 0:
+            return self.empty(0)
+        host = torch.frombuffer(buf, dtype=torch.int64).reshape(-1, 2)
+        return host.to(self.device)
+
+    def download(self, vec):
+        """device vector -> numpy uint64[n, 2] (buffer protocol, 16 bytes/element)"""
+        return vec.contiguous().cpu().numpy()
+
+    def pad(self, vec, n):
+        """zero-extend to n elements"""
+        if vec.shape[0] == n:
+            return vec
+        out = self.zeros(n)
+        out[:vec.shape[0]] = vec
+        return out
+
+    def slice(self, vec, lo, hi):
+        return vec[lo:hi]
+
+    def concat(self, vecs):
+        return self.torch.cat(vecs, dim=0)
+
+    # ------------------------------------------------------------------ ntt
+    def ntt(self, vec, log_n, root, inverse=False, batch=1):
+        vec = vec.contiguous()
+        out = self.empty(vec.shape[0])
+        self._check(self.lib.sa_ntt(out.data_ptr(), vec.data_ptr(), log_n, _limbs(root), int(bool(inverse)),
+                                    batch, self._stream()))
+        return out
+
+    def pointwise_mul(self, a, b):
+        out = self.empty(a.shape[0])
+        self._check(self.lib.sa_pointwise_mul(out.data_ptr(), a.contiguous().data_ptr(),
+                                              b.contiguous().data_ptr(), a.shape[0], self._stream()))
+        return out
+
+    def pointwise_div(self, a, b):
+        out = self.empty(a.shape[0])
+        self._check(self.lib.sa_pointwise_div(out.data_ptr(), a.contiguous().data_ptr(),
+                                              b.contiguous().data_ptr(), a.shape[0], self._stream()))
+        return out
+
+    def scale(self, vec, factor):
+        vec = vec.contiguous()
+        out = self.empty(vec.shape[0])
+        self._check(self.lib.sa_scale(out.data_ptr(), vec.data_ptr(), vec.shape[0], _limbs(factor), self._stream()))
+        return out
+
+    def poly_eval(self, coeffs, points):
+        coeffs, points = coeffs.contiguous(), points.contiguous()
+        out = self.empty(points.shape[0])
+        self._check(self.lib.sa_poly_eval(out.data_ptr(), coeffs.data_ptr(), coeffs.shape[0], points.data_ptr(),
+                                          points.shape[0], self._stream()))
+        return out
+
+    # --------------------------------------------------------------- merkle
+    def _new_tree(self, n):
+        return self.torch.empty((2 * n, 64), dtype=self.torch.uint8, device=self.device)
+
+    def merkle_tree(self, vec):
+        vec = vec.contiguous()
+        n = vec.shape[0]
+        tree = self._new_tree(n)
+        self._check(self.lib.sa_merkle_tree(tree.data_ptr(), vec.data_ptr(), n, self._stream()))
+        return tree
+
+    def tree_root(self, tree):
+        return bytes(tree[1].cpu().numpy().tobytes())
+
+    def merkle_open(self, tree, indices):
+        """authentication paths (lists of 64-byte digests, bottom-up) for leaf indices"""
+        n = tree.shape[0] // 2
+        k = len(indices)
+        depth = n.bit_length() - 1
+        if k == 0:
+            return []
+        if depth == 0:
+            for i in indices:
+                if not 0 <= i < n:
+                    raise SaError(SA_ERRORS[-5])
+            return [[] for _ in indices]
+        for i in indices:
+            if not 0 <= i < n:
+                raise SaError(SA_ERRORS[-5])
+        out = self.torch.empty((k, depth, 64), dtype=self.torch.uint8, device=self.device)
+        idx = (ctypes.c_uint64 * k)(*indices)
+        self._check(self.lib.sa_merkle_open(out.data_ptr(), tree.data_ptr(), n, idx, k, self._stream()))
+        raw = out.cpu().numpy().tobytes()
+        return [[raw[(q * depth + l) * 64:(q * depth + l + 1) * 64] for l in range(depth)] for q in range(k)]
+
+    def gather(self, vec, indices):
+        """values at `indices` -> numpy uint64[k, 2] on the host"""
+        vec = vec.contiguous()
+        k = len(indices)
+        out = self.empty(k)
+        if k:
+            idx = (ctypes.c_uint64 * k)(*indices)
+            self._check(self.lib.sa_gather(out.data_ptr(), vec.data_ptr(), vec.shape[0], idx, k, self._stream()))
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ fri
+    def fri_fold(self, vec, alpha, offset, omega):
+        vec = vec.contiguous()
+        n = vec.shape[0]
+        out = self.empty(n // 2)
+        self._check(self.lib.sa_fri_fold(out.data_ptr(), vec.data_ptr(), n, _limbs(alpha), _limbs(offset),
+                                         _limbs(omega), self._stream()))
+        return out
+
+    def fri_round(self, vec, alpha, offset, omega):
+        """fold (fri.py:85) + Merkle tree of the folded codeword, one fused kernel"""
+        vec = vec.contiguous()
+        n = vec.shape[0]
+        out = self.empty(n // 2)
+        tree = self._new_tree(n // 2)
+        self._check(self.lib.sa_fri_round(out.data_ptr(), tree.data_ptr(), vec.data_ptr(), n, _limbs(alpha),
+                                          _limbs(offset), _limbs(omega), self._stream()))
+        return out, tree
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
+    def launch_count(self):
+        return int(self.lib.sa_launch_count())
+
+
+_ENGINE = None
+
+
+def get_engine():
+    """The process-wide engine; created on first use.  Raises without CUDA."""
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = CudaEngine()
+    return _ENGINE
+
+
+def set_engine(engine):
+    """Install an engine object (tests use this to exercise the host logic with a
+    test double; the product never calls it)."""
+    global _ENGINE
+    _ENGINE = engine
+    return engine

@@ -1,0 +1,234 @@
+"""Parity cases for the drop-in ``ntt`` / ``fri`` modules against tests/golden/*.json
+(the reference's own outputs).  The same functions run twice:
+
+  * tests/test_dropin_cpu.py  -- engine = tests/fake_engine.OracleEngine: checks the HOST
+    logic (marshalling, list lengths, assertion messages, proof-stream pushes and
+    pickle identity) without a GPU;
+  * tests/test_dropin_gpu.py  -- engine = the CUDA engine: the parity tests proper.
+"""
+import hashlib
+import pickle
+import random
+
+import pytest
+
+from conftest import load_golden
+from hostmirror_loader import load_host_types
+
+T = load_host_types()
+import ntt as N  # noqa: E402  (the drop-in, stark-anatomy_b200/ntt.py)
+import fri as F  # noqa: E402
+
+P = T.field.p
+
+
+def vals(xs):
+    return [x.value for x in xs]
+
+
+def digest(xs):
+    return hashlib.blake2b(b"".join(x.value.to_bytes(16, "little") for x in xs)).hexdigest()
+
+
+def seeded(seed, n):
+    rng = random.Random(seed)
+    return [T.fe(rng.randrange(P)) for _ in range(n)]
+
+
+# ------------------------------------------------------------------------ ntt
+def case_ntt_vectors():
+    g = load_golden("ntt.json")
+    for c in g["ntt"]:
+        xs = T.elems(c["in"])
+        out = N.ntt(T.fe(c["root"]), xs)
+        assert vals(out) == [int(v) for v in c["out"]], f"ntt n={c['n']} seed={c['seed']}"
+        if c["n"] <= 1:
+            assert out is xs  # ntt.py:5-6 returns the argument itself
+        else:
+            assert out is not xs and all(type(o) is T.FieldElement and o.field is T.field for o in out)
+    for c in g["intt"]:
+        xs = T.elems(c["in"])
+        assert vals(N.intt(T.fe(c["root"]), xs)) == [int(v) for v in c["out"]], f"intt n={c['n']}"
+    one = [T.fe(5)]
+    assert N.intt(T.field.primitive_nth_root(1), one) is one
+
+
+def case_ntt_asserts():
+    with pytest.raises(AssertionError, match="cannot compute ntt of non-power-of-two sequence"):
+        N.ntt(T.field.primitive_nth_root(4), T.elems([1, 2, 3]))
+    with pytest.raises(AssertionError, match="cannot compute intt of non-power-of-two sequence"):
+        N.intt(T.field.primitive_nth_root(4), T.elems([1, 2, 3]))
+    with pytest.raises(AssertionError, match="primitive root must be nth root of unity"):
+        N.ntt(T.field.primitive_nth_root(8), T.elems([1, 2, 3, 4]))
+    with pytest.raises(AssertionError, match="primitive root is not primitive nth root of unity"):
+        N.ntt(T.field.primitive_nth_root(2), T.elems([1, 2, 3, 4]))
+
+
+def case_ntt_digests(max_n):
+    for c in load_golden("ntt.json")["digests"]:
+        if c["n"] > max_n:
+            continue
+        xs = seeded(c["seed"], c["n"])
+        w = T.fe(c["root"])
+        ys = N.ntt(w, xs)
+        assert digest(ys) == c["ntt"], f"ntt digest n={c['n']}"
+        if "intt" in c:
+            assert digest(N.intt(w, xs)) == c["intt"]
+        assert vals(N.intt(w, ys)) == vals(xs)  # round trip
+
+
+def case_poly():
+    g = load_golden("poly.json")
+    for c in g["multiply"]:
+        got = N.fast_multiply(T.poly(c["lhs"]), T.poly(c["rhs"]), T.fe(c["root"]), c["order"])
+        assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_multiply"
+    for c in g["coset_evaluate"]:
+        got = N.fast_coset_evaluate(T.poly(c["coeffs"]), T.fe(c["offset"]), T.fe(c["generator"]), c["order"])
+        assert vals(got) == [int(v) for v in c["out"]], "fast_coset_evaluate"
+    for c in g["coset_divide"]:
+        got = N.fast_coset_divide(T.poly(c["lhs"]), T.poly(c["rhs"]), T.fe(c["offset"]), T.fe(c["root"]), c["order"])
+        assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_coset_divide"
+    for c in g["zerofier"]:
+        got = N.fast_zerofier(T.elems(c["domain"]), T.fe(c["root"]), c["order"])
+        assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_zerofier"
+    for c in g["evaluate"]:
+        got = N.fast_evaluate(T.poly(c["coeffs"]), T.elems(c["domain"]), T.fe(c["root"]), c["order"])
+        assert vals(got) == [int(v) for v in c["out"]], "fast_evaluate"
+    for c in g["interpolate"]:
+        got = N.fast_interpolate(T.elems(c["domain"]), T.elems(c["values"]), T.fe(c["root"]), c["order"])
+        assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_interpolate"
+
+
+def case_poly_asserts():
+    w = T.field.primitive_nth_root(64)
+    a, b = T.poly(range(1, 20)), T.poly(range(3, 12))
+    with pytest.raises(AssertionError, match="supplied root does not have supplied order"):
+        N.fast_multiply(a, b, w, 32)
+    with pytest.raises(AssertionError, match="supplied root is not primitive root of supplied order"):
+        N.fast_multiply(a, b, w, 128)
+    with pytest.raises(AssertionError, match="cannot divide by zero polynomial"):
+        N.fast_coset_divide(a, T.poly([0, 0]), T.field.generator(), w, 64)
+    with pytest.raises(AssertionError, match="cannot divide by polynomial of larger degree"):
+        N.fast_coset_divide(b, a, T.field.generator(), w, 64)
+    with pytest.raises(AssertionError, match="cannot interpolate over domain of different length"):
+        N.fast_interpolate(T.elems([1, 2]), T.elems([1]), w, 64)
+    # a divisor codeword with a zero entry: algebra.py:92 "divide by zero"
+    zero_at_coset = T.poly([(-T.field.generator()).value, 1])  # X - g vanishes at g*w^0
+    big = T.poly(range(1, 30))
+    with pytest.raises(AssertionError, match="divide by zero"):
+        N.fast_coset_divide(big * T.poly([1] * 9), zero_at_coset * T.poly([1] * 9), T.field.generator(), w, 64)
+
+
+def case_fast_multiply_big(n):
+    c = [c for c in load_golden("poly.json")["big"] if c["n"] == n][0]
+    rng = random.Random(c["seed"])
+    lhs = T.Polynomial([T.fe(rng.randrange(P)) for _ in range(n // 2)])
+    rhs = T.Polynomial([T.fe(rng.randrange(P)) for _ in range(n // 2)])
+    got = N.fast_multiply(lhs, rhs, T.field.primitive_nth_root(n), n)
+    assert len(got.coefficients) == n - 1
+    assert digest(got.coefficients) == c["digest"]
+
+
+# ------------------------------------------------------------------------ fri
+def case_fri_commit(max_n):
+    for c in load_golden("fri.json")["commit"]:
+        if c["n"] > max_n or "roots" not in c:
+            continue
+        n = c["n"]
+        cw = seeded(c["seed"], n)
+        fri = F.Fri(T.field.generator(), T.field.primitive_nth_root(n), n, c["ef"], c["tests"])
+        assert fri.num_rounds() == c["rounds"]
+        ps = F.ProofStream()
+        layers = fri.commit(cw, ps)
+        roots = [o for o in ps.objects if isinstance(o, bytes)]
+        assert [r.hex() for r in roots] == c["roots"]
+        assert type(ps.objects[-1]) is list and vals(ps.objects[-1]) == [int(v) for v in c["last"]]
+        assert layers[0] is cw and layers[-1] is ps.objects[-1]  # fri.py:82,91-96 aliasing
+        assert [len(l) for l in layers] == c["layer_lens"]
+        assert [digest(list(l)) for l in layers] == c["layer_digests"]
+        assert hashlib.sha256(pickle.dumps(ps.objects)).hexdigest() == c["transcript_sha256"]
+
+
+def case_fri_commit_2_20():
+    c = [c for c in load_golden("fri.json")["commit"] if c["n"] == 1 << 20][0]
+    n = 1 << 20
+    cw = seeded(1, n)
+    fri = F.Fri(T.field.generator(), T.field.primitive_nth_root(n), n, 4, 64)
+    ps = F.ProofStream()
+    fri.commit(cw, ps)
+    roots = [o for o in ps.objects if isinstance(o, bytes)]
+    assert [r[:8].hex() for r in roots] == c["roots8"]
+
+
+def case_fri_prove(max_n, with_verify=True):
+    for c in load_golden("fri.json")["prove"]:
+        if c["n"] > max_n:
+            continue
+        n = c["n"]
+        omega = T.field.primitive_nth_root(n)
+        g = T.field.generator()
+        codeword = N.fast_coset_evaluate(T.poly(c["coeffs"]), g, omega, n)
+        fri = F.Fri(g, omega, n, c["ef"], c["tests"])
+        ps = F.ProofStream()
+        ps.push(b"prior-object")
+        indices = fri.prove(codeword, ps)
+        assert indices == c["indices"]
+        assert len(ps.objects) == c["num_objects"]
+        if "objects" in c:
+            want = [T.dec_obj(o) for o in c["objects"]]
+            for i, (got_o, want_o) in enumerate(zip(ps.objects, want)):
+                assert pickle.dumps(got_o) == pickle.dumps(want_o), f"object {i} differs"
+        else:
+            assert [hashlib.sha256(pickle.dumps(o)).hexdigest() for o in ps.objects] == c["object_sha256"]
+        # byte-identical transcript, including pickle's object-identity (memo) structure
+        assert hashlib.sha256(pickle.dumps(ps.objects)).hexdigest() == c["transcript_sha256"]
+        if with_verify and n <= 1024:
+            vs = F.ProofStream()
+            vs.objects = list(ps.objects)
+            vs.pull()
+            points = []
+            assert fri.verify(vs, points) is True
+            for (i, y) in points:  # returned points lie on the polynomial (test_fri.py:44-50)
+                assert T.poly(c["coeffs"]).evaluate(g * (omega ^ i)) == y
+            # corrupt the codeword -> verifier must reject (test_fri.py:52-58)
+            bad = list(codeword)
+            for i in range(0, n // 3):
+                bad[i] = T.field.zero()
+            bs = F.ProofStream()
+            fri.prove(bad, bs)
+            assert fri.verify(bs, []) is False
+
+
+def case_faststark_trace_replay():
+    """Replay every call fast_stark.py made into the ntt/fri surfaces during a seeded
+    FastStark.prove (recorded from the unmodified reference) and compare results."""
+    g = load_golden("faststark_trace.json")
+
+    def dec(a):
+        (k, v), = a.items()
+        if k == "poly":
+            return T.poly(v)
+        if k == "f":
+            return T.fe(v)
+        if k == "l":
+            return T.elems(v)
+        return v
+    for call in g["calls"]:
+        args = [dec(a) for a in call["args"]]
+        got = getattr(N, call["fn"])(*args)
+        (k, want), = call["out"].items()
+        got_vals = vals(got.coefficients) if k == "poly" else vals(got)
+        assert got_vals == [int(v) for v in want], call["fn"]
+    p = g["params"]
+    for rec in g["fri_prove"]:
+        n = p["fri_domain_length"]
+        fri = F.Fri(T.field.generator(), T.field.primitive_nth_root(n), n, p["expansion_factor"],
+                    p["num_colinearity_checks"])
+        ps = F.ProofStream()
+        ps.objects = [T.dec_obj(o) for o in rec["prior_objects"]]
+        assert hashlib.sha256(pickle.dumps(ps.objects)).hexdigest() == rec["prior_sha256"]
+        before = len(ps.objects)
+        idx = fri.prove(T.elems(rec["codeword"]), ps)
+        assert idx == rec["indices"]
+        want = [T.dec_obj(o) for o in rec["pushed"]]
+        assert [pickle.dumps(o) for o in ps.objects[before:]] == [pickle.dumps(o) for o in want]

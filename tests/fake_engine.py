@@ -1,0 +1,115 @@
+"""TEST DOUBLE for sa_engine.CudaEngine, backed by the CPU oracle.
+
+It lets the ``not gpu`` tests drive the drop-in modules' HOST logic (marshalling,
+list-length semantics, proof-stream pushes and object identity, assertion
+messages) in this GPU-less container -- including running the reference's
+unmodified code/fast_stark.py against the drop-in.  It lives in tests/ and is
+installed with ``sa_engine.set_engine`` by tests only; the product's default
+engine is the CUDA one and has no fallback.
+"""
+import numpy as np
+
+import oracle as O
+from sa_engine import SA_ERRORS, SaError
+
+
+class OracleEngine:
+    name = "oracle-test-double"
+
+    def __init__(self):
+        self.calls = []
+
+    def _log(self, name, *shape):
+        self.calls.append((name,) + shape)
+
+    # -------------------------------------------------------------- plumbing
+    def empty(self, n):
+        return np.zeros((n, 2), dtype=np.uint64)
+
+    zeros = empty
+
+    def length(self, vec):
+        return vec.shape[0]
+
+    def upload(self, buf):
+        if isinstance(buf, np.ndarray):
+            return buf.reshape(-1, 2).astype(np.uint64)
+        return np.frombuffer(bytes(buf), dtype="<u8").reshape(-1, 2).copy()
+
+    def download(self, vec):
+        return np.ascontiguousarray(vec)
+
+    def pad(self, vec, n):
+        out = np.zeros((n, 2), dtype=np.uint64)
+        out[:vec.shape[0]] = vec
+        return out
+
+    def slice(self, vec, lo, hi):
+        return vec[lo:hi]
+
+    def concat(self, vecs):
+        return np.concatenate(vecs, axis=0)
+
+    # ------------------------------------------------------------------- ops
+    def ntt(self, vec, log_n, root, inverse=False, batch=1):
+        self._log("ntt", log_n, inverse, batch)
+        n = 1 << log_n
+        assert vec.shape[0] == n * batch
+        fn = O.intt_np if inverse else O.ntt_np
+        try:
+            return np.concatenate([fn(root, vec[b * n:(b + 1) * n]) for b in range(batch)], axis=0)
+        except AssertionError as e:
+            raise SaError(str(e))
+
+    def pointwise_mul(self, a, b):
+        self._log("pointwise_mul", a.shape[0])
+        return O.pointwise_mul_np(np.ascontiguousarray(a), np.ascontiguousarray(b))
+
+    def pointwise_div(self, a, b):
+        self._log("pointwise_div", a.shape[0])
+        try:
+            return O.pointwise_div_np(np.ascontiguousarray(a), np.ascontiguousarray(b))
+        except AssertionError:
+            raise SaError(SA_ERRORS[-4])
+
+    def scale(self, vec, factor):
+        self._log("scale", vec.shape[0])
+        return O.scale_np(vec, factor) if vec.shape[0] else vec
+
+    def poly_eval(self, coeffs, points):
+        self._log("poly_eval", coeffs.shape[0], points.shape[0])
+        return O.poly_eval_np(coeffs, points)
+
+    def merkle_tree(self, vec):
+        self._log("merkle_tree", vec.shape[0])
+        return O.merkle_tree_np(vec)
+
+    def tree_root(self, tree):
+        return tree[1].tobytes()
+
+    def merkle_open(self, tree, indices):
+        self._log("merkle_open", len(indices))
+        n = tree.shape[0] // 2
+        for i in indices:
+            if not 0 <= i < n:
+                raise SaError(SA_ERRORS[-5])
+        return [O.merkle_open(tree, i) if n > 1 else [] for i in indices]
+
+    def gather(self, vec, indices):
+        self._log("gather", len(indices))
+        return np.ascontiguousarray(vec[list(indices)]) if len(indices) else np.zeros((0, 2), np.uint64)
+
+    def fri_fold(self, vec, alpha, offset, omega):
+        self._log("fri_fold", vec.shape[0])
+        return O.fri_fold_np(vec, alpha, offset, omega)
+
+    def fri_round(self, vec, alpha, offset, omega):
+        self._log("fri_round", vec.shape[0])
+        nxt = O.fri_fold_np(vec, alpha, offset, omega)
+        return nxt, O.merkle_tree_np(nxt)
+
+    def synchronize(self):
+        pass
+
+    def launch_count(self):
+        return 0

@@ -1,0 +1,115 @@
+"""Host-logic tests of the drop-in modules (no GPU): the engine is replaced by the
+oracle-backed test double from tests/fake_engine.py.  Everything here is checked
+against the reference's own outputs in tests/golden/."""
+import hashlib
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+import dropin_cases as C
+import sa_engine
+from fake_engine import OracleEngine
+from conftest import load_golden, ROOT
+from hostmirror_loader import REFERENCE
+
+
+@pytest.fixture(autouse=True)
+def double_engine():
+    prev = sa_engine._ENGINE
+    sa_engine.set_engine(OracleEngine())
+    yield
+    sa_engine.set_engine(prev)
+
+
+def test_ntt_vectors():
+    C.case_ntt_vectors()
+
+
+def test_ntt_asserts():
+    C.case_ntt_asserts()
+
+
+def test_ntt_digests():
+    C.case_ntt_digests(1 << 14)
+
+
+def test_poly():
+    C.case_poly()
+
+
+def test_poly_asserts():
+    C.case_poly_asserts()
+
+
+def test_fast_multiply_4096():
+    C.case_fast_multiply_big(1 << 12)
+
+
+def test_fri_commit():
+    C.case_fri_commit(1 << 12)
+
+
+def test_fri_prove_and_verify():
+    C.case_fri_prove(1 << 12)
+
+
+def test_faststark_trace_replay():
+    C.case_faststark_trace_replay()
+
+
+def test_engine_use_is_recorded():
+    """the drop-in really goes through the engine object (no hidden host arithmetic)"""
+    eng = sa_engine.get_engine()
+    C.N.ntt(C.T.field.primitive_nth_root(16), C.seeded(1, 16))
+    assert ("ntt", 4, False, 1) in eng.calls
+
+
+def test_default_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sa_engine.set_engine(None)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        C.N.ntt(C.T.field.primitive_nth_root(16), C.seeded(1, 16))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_unmodified_fast_stark_prove_is_byte_identical():
+    """code/fast_stark.py, UNMODIFIED, imported with the drop-in ahead of it on sys.path:
+    with os.urandom seeded as in tests/golden/make_golden.py the proof must be the same
+    bytes the pure reference produced, and the reference verifier must accept it."""
+    code = r'''
+import sys, os, random, hashlib
+sys.dont_write_bytecode = True
+sys.path[:0] = [%(pkg)r, %(ref)r, %(oracle)r, %(tests)r]
+import sa_engine
+from fake_engine import OracleEngine
+sa_engine.set_engine(OracleEngine())
+import fast_stark as fs, fri, ntt
+assert fri.__file__.startswith(%(pkg)r) and ntt.__file__.startswith(%(pkg)r)
+assert fs.__file__.startswith(%(ref)r)
+assert fs.fast_coset_evaluate is ntt.fast_coset_evaluate and fs.Fri is fri.Fri
+from rescue_prime import RescuePrime
+from algebra import Field, FieldElement
+field = Field.main()
+rng = random.Random(600)
+os.urandom = lambda n: bytes(rng.getrandbits(8) for _ in range(n))
+rp = RescuePrime()
+stark = fs.FastStark(field, 4, 2, 2, rp.m, rp.N + 1, transition_constraints_degree=3)
+tz, tzc, tzr = stark.preprocess()
+x = FieldElement(rng.randrange(field.p), field)
+trace = rp.trace(x)
+air = rp.transition_constraints(stark.omicron)
+boundary = rp.boundary_constraints(rp.hash(x))
+proof = stark.prove(trace, air, boundary, tz, tzc)
+ok = stark.verify(proof, air, boundary, tzr)
+print(hashlib.sha256(proof).hexdigest(), len(proof), ok, len(sa_engine.get_engine().calls))
+''' % {"pkg": os.path.join(ROOT, "stark-anatomy_b200"), "ref": REFERENCE,
+       "oracle": os.path.join(ROOT, "oracle"), "tests": os.path.join(ROOT, "tests")}
+    out = subprocess.check_output([sys.executable, "-c", code], text=True).split()
+    g = load_golden("faststark_trace.json")
+    assert out[0] == g["proof_sha256"] and int(out[1]) == g["proof_len"]
+    assert out[2] == "True" and int(out[3]) > 10

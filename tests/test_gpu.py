@@ -1,0 +1,227 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every check goes through the
+C ABI (include/sa_b200.h) via sa_engine's ctypes binding and is compared bit-exactly with
+the CPU oracle on the same seeded inputs, with the reference's golden digests, or through
+size-independent properties at BASELINE.json's full sizes."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+import dropin_cases as C
+import sa_engine
+
+pytestmark = pytest.mark.gpu
+P = O.P
+
+
+@pytest.fixture(scope="module")
+def eng():
+    sa_engine.set_engine(None)
+    e = sa_engine.get_engine()  # raises without CUDA / without the built library
+    assert e.name == "cuda"
+    return e
+
+
+@pytest.fixture(autouse=True)
+def _cuda_engine(eng):
+    sa_engine.set_engine(eng)
+    yield
+
+
+def rand_np(seed, n):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+    hi = rng.integers(0, 0xCB80000000000000, size=n, dtype=np.uint64)  # < p's top limb => < p
+    return np.stack([lo, hi], axis=1)
+
+
+def up(eng, arr):
+    return eng.upload(np.ascontiguousarray(arr).view(np.int64))
+
+
+def down(eng, vec):
+    return eng.download(vec).view(np.uint64)
+
+
+def test_field_selftest(eng):
+    assert eng.lib.sa_selftest_field(1 << 20, 12345) == 0
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 21)))
+def test_ntt_matches_oracle(eng, log_n):
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    for batch in ([1, 3, 17] if log_n <= 12 else [1, 2] if log_n <= 16 else [1]):
+        x = rand_np(1000 + log_n, n * batch)
+        for inverse in (False, True):
+            got = down(eng, eng.ntt(up(eng, x), log_n, w, inverse=inverse, batch=batch))
+            for b in range(batch):
+                xb = x[b * n:(b + 1) * n]
+                want = O.intt_np(w, xb, parallel=True) if inverse else O.ntt_np(w, xb, parallel=True)
+                assert (got[b * n:(b + 1) * n] == want).all(), (log_n, batch, inverse, b)
+
+
+def test_ntt_edge_inputs_and_roots(eng):
+    for log_n in (3, 10, 13):
+        n = 1 << log_n
+        w = O.primitive_nth_root(n)
+        for name, x in (("zeros", np.zeros((n, 2), np.uint64)),
+                        ("pm1", O.to_np([P - 1] * n)), ("delta", O.to_np([1] + [0] * (n - 1)))):
+            assert (down(eng, eng.ntt(up(eng, x), log_n, w)) == O.ntt_np(w, x)).all(), name
+        w2 = pow(w, 3, P)  # any primitive root, e.g. the squared roots fast_multiply derives
+        x = rand_np(5, n)
+        assert (down(eng, eng.ntt(up(eng, x), log_n, w2)) == O.ntt_np(w2, x)).all()
+    x = up(eng, rand_np(6, 16))
+    with pytest.raises(AssertionError, match="primitive root must be nth root of unity"):
+        eng.ntt(x, 4, O.primitive_nth_root(64))
+    with pytest.raises(AssertionError, match="not primitive nth root"):
+        eng.ntt(x, 4, O.primitive_nth_root(4))
+
+
+def test_ntt_in_place_and_host_entry(eng):
+    import torch
+    log_n, batch = 14, 4
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    x = rand_np(77, n * batch)
+    v = up(eng, x)
+    rc = eng.lib.sa_ntt(v.data_ptr(), v.data_ptr(), log_n, sa_engine._limbs(w), 0, batch, eng._stream())
+    assert rc == 0
+    want = O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2)
+    assert (down(eng, v) == want).all()
+    out = np.zeros_like(x)
+    rc = eng.lib.sa_ntt_host(out.ctypes.data, x.ctypes.data, log_n, sa_engine._limbs(w), 0, batch, eng._stream())
+    assert rc == 0 and (out == want).all()
+    torch.cuda.synchronize()
+
+
+def test_ntt_2_20_golden_digest_and_roundtrip(eng):
+    C.case_ntt_digests(1 << 20)
+
+
+def test_ntt_2_20_batch_properties(eng):
+    """full-size, size-independent properties: round trip and linearity on a batch of 2^20 transforms"""
+    log_n, batch = 20, 4
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    x = rand_np(21, n * batch)
+    vx = up(eng, x)
+    y = eng.ntt(vx, log_n, w, batch=batch)
+    back = eng.ntt(y, log_n, w, inverse=True, batch=batch)
+    assert bool((back == vx).all())
+    # ntt(a) + ntt(b) == ntt(a + b) on the first two batch items (sum taken by the oracle's field add)
+    a, b = x[:n], x[n:2 * n]
+    s = O.to_np([(u + v) % P for u, v in zip(O.from_np(a[:4096]), O.from_np(b[:4096]))])
+    ya, yb = down(eng, y[:n]), down(eng, y[n:2 * n])
+    full_sum = O.pointwise_mul_np(np.ascontiguousarray(a), O.to_np([1] * n))  # copy through the oracle
+    assert (full_sum == a).all()
+    got_sum = down(eng, eng.ntt(up(eng, _field_add(a, b)), log_n, w))
+    assert (got_sum == _field_add(ya, yb)).all()
+    assert (s == _field_add(a[:4096], b[:4096])).all()
+
+
+def _field_add(a, b):
+    """vectorised (a + b) mod p on uint64[n,2] (numpy, test-side helper)"""
+    alo, ahi = a[:, 0].astype(object), a[:, 1].astype(object)
+    blo, bhi = b[:, 0].astype(object), b[:, 1].astype(object)
+    s = (alo + (ahi << 64)) + (blo + (bhi << 64))
+    s = np.where(s >= P, s - P, s)
+    return np.stack([(s & 0xFFFFFFFFFFFFFFFF).astype(np.uint64), (s >> 64).astype(np.uint64)], axis=1)
+
+
+def test_elementwise_ops(eng):
+    for n in (1, 7, 1000, 1 << 16):
+        a, b = rand_np(31, n), rand_np(32, n)
+        b[b.sum(axis=1) == 0] = 1
+        assert (down(eng, eng.pointwise_mul(up(eng, a), up(eng, b))) == O.pointwise_mul_np(a, b)).all()
+        if n <= 1 << 12:
+            assert (down(eng, eng.pointwise_div(up(eng, a), up(eng, b))) == O.pointwise_div_np(a, b)).all()
+        f = random.Random(n).randrange(P)
+        assert (down(eng, eng.scale(up(eng, a), f)) == O.scale_np(a, f)).all()
+    a, b = rand_np(33, 4096), rand_np(34, 4096)
+    b[1234] = 0
+    with pytest.raises(AssertionError, match="divide by zero"):
+        eng.pointwise_div(up(eng, a), up(eng, b))
+    coeffs, pts = rand_np(35, 300), rand_np(36, 517)
+    assert (down(eng, eng.poly_eval(up(eng, coeffs), up(eng, pts))) == O.poly_eval_np(coeffs, pts)).all()
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 9, 10, 11, 14, 17])
+def test_merkle_tree_and_open(eng, log_n):
+    n = 1 << log_n
+    x = rand_np(50 + log_n, n)
+    x[0] = 0
+    if n > 4:
+        x[1] = (7, 0)
+        x[2] = O._fe(10**19)
+        x[3] = O._fe(P - 1)
+    tree = eng.merkle_tree(up(eng, x))
+    want = O.merkle_tree_np(x)
+    assert (tree.cpu().numpy()[1:] == want[1:]).all()
+    assert eng.tree_root(tree) == want[1].tobytes()
+    if n >= 2:
+        idx = sorted({0, 1, n // 2, n - 1, random.Random(log_n).randrange(n)})
+        assert eng.merkle_open(tree, idx) == [O.merkle_open(want, i) for i in idx]
+        assert (eng.gather(up(eng, x), idx).view(np.uint64) == x[idx]).all()
+        with pytest.raises(AssertionError, match="cannot open invalid index"):
+            eng.merkle_open(tree, [n])
+
+
+def test_merkle_root_2_20_golden(eng):
+    from conftest import load_golden
+    c = [m for m in load_golden("merkle.json")["commit"] if m["n"] == 1 << 20][0]
+    xs = C.seeded(1, 1 << 20)
+    import sa_marshal
+    tree = eng.merkle_tree(eng.upload(sa_marshal.pack(xs)))
+    assert eng.tree_root(tree).hex() == c["root"]
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 6, 10, 11, 15])
+def test_fri_round_and_fold(eng, log_n):
+    n = 1 << log_n
+    x = rand_np(60 + log_n, n)
+    rng = random.Random(log_n)
+    alpha, omega, off = rng.randrange(P), O.primitive_nth_root(n), O.GENERATOR
+    want = O.fri_fold_np(x, alpha, off, omega)
+    assert (down(eng, eng.fri_fold(up(eng, x), alpha, off, omega)) == want).all()
+    nxt, tree = eng.fri_round(up(eng, x), alpha, off, omega)
+    assert (down(eng, nxt) == want).all()
+    assert (tree.cpu().numpy()[1:] == O.merkle_tree_np(want)[1:]).all()
+
+
+# ---- the drop-in modules on the real engine, against the reference's golden outputs -------
+def test_dropin_ntt_vectors(eng):
+    C.case_ntt_vectors()
+    C.case_ntt_asserts()
+
+
+def test_dropin_poly(eng):
+    C.case_poly()
+    C.case_poly_asserts()
+
+
+def test_dropin_fast_multiply_digests(eng):
+    C.case_fast_multiply_big(1 << 12)
+    C.case_fast_multiply_big(1 << 20)  # BASELINE.md section 3 (654 s of reference time)
+
+
+def test_dropin_fri_commit(eng):
+    C.case_fri_commit(1 << 12)
+
+
+def test_dropin_fri_commit_2_20_golden_roots(eng):
+    C.case_fri_commit_2_20()  # BASELINE.md section 3 (73.1 s of reference time)
+
+
+def test_dropin_fri_prove_and_verify(eng):
+    C.case_fri_prove(1 << 12)
+
+
+def test_dropin_faststark_trace_replay(eng):
+    C.case_faststark_trace_replay()
+
+
+def test_kernels_were_launched(eng):
+    assert eng.launch_count() > 100

