@@ -1,20 +1,27 @@
 // ntt_tile.cuh -- the NTT building block: L-point transforms (L = 2^LOGL <= 1024)
-// on a tile of 8 columns, natural order in, natural order out.
+// on a tile of C columns, natural order in, natural order out.
 // Reproduces code/ntt.py:3-18 (out[i] = sum_j v[j] * w^(i*j)); bit-exact because
 // every operation is exact arithmetic on canonical residues (field.cuh).
 //
 // Algorithm (Blackwell-first, not the reference's recursion): mixed-radix
-// decimation with radix-16 register blocks.  A thread owns 16 elements of one
-// column, runs a complete 16-point (or 2/4/8-point) transform in registers,
+// decimation with register blocks of E = 2^ELOG elements (E = 16 or 8).  A thread
+// owns E elements of one column, runs a complete E-point transform in registers,
 // applies the inter-stage twiddle, and exchanges through shared memory only
-// between register blocks (two exchanges for L = 1024).  All stages work in
-// place on tile row p = K*M' + d*M + m (d = the digit being transformed), so the
-// first block loads straight from global memory into registers and the last one
-// stores straight from registers, digit-reversed, to the natural output index.
+// between register blocks.  All stages work in place on tile row
+// p = K*M' + d*M + m (d = the digit being transformed), so the first block loads
+// straight from global memory into registers and the last one stores straight
+// from registers, digit-reversed, to the natural output index.
 //
-// A tile row is 8 columns x 16 bytes = one 128-byte line: lanes 0-7 of every
-// quarter warp cover a full row, so every shared-memory access is conflict free
-// and every global access is a full 128-byte (or 64-byte, see ntt.cu) segment.
+// The full-radix stages share ONE copy of the E-point transform code (a rolled
+// loop with run-time strides), which keeps the kernel inside the instruction
+// cache; only the first (global loads) and last (output twiddle + global stores)
+// differ.
+//
+// A tile row is C columns x 16 bytes.  With C = 8 a row is one 128-byte line:
+// lanes 0-7 of every quarter warp cover a full row, every shared-memory access
+// is conflict free and every global access is a full line.  C = 4 / 2 give 64 /
+// 32-byte segments (still whole sectors) with smaller tiles, i.e. more
+// independent CTAs per SM.
 //
 // The functions are __host__ __device__: tests/emu runs exactly this code on the
 // CPU, thread by thread and phase by phase.
@@ -22,8 +29,6 @@
 #include "field.cuh"
 
 namespace sa {
-
-constexpr int TILE_C = 8;
 
 struct TileArgs {
     const fe *in;
@@ -37,26 +42,23 @@ struct TileArgs {
     int nbatch;  // batch items
     int has_scale;
     fe scale;   // Montgomery-form scalar applied to every output when has_scale
-    fe cst[8];  // cst[k] = w_Rmax^k (Montgomery form), Rmax = min(16, L), k < Rmax/2
+    fe cst[8];  // cst[k] = w_16^k (Montgomery form) when L >= 16, else w_L^k; k < 8
 };
 
-template <int LOGL>
+template <int LOGL, int ELOG, int C>
 struct TilePlan {
     static constexpr int L = 1 << LOGL;
-    static constexpr int NST = (LOGL + 3) / 4;
-    static constexpr int E = L >= 16 ? 16 : L;       // elements per thread
-    static constexpr int TPT = (L / E) * TILE_C;     // threads per tile
+    static constexpr int EL = LOGL >= ELOG ? ELOG : LOGL;  // log2 elements per thread
+    static constexpr int E = 1 << EL;
+    static constexpr int NFULL = LOGL / EL;        // stages of radix E
+    static constexpr int REM = LOGL % EL;          // log2 radix of the trailing stage (0 = none)
+    static constexpr int NST = NFULL + (REM ? 1 : 0);
+    static constexpr int NLOOP = NST - 1;          // full-radix stages that are not the last stage
+    static constexpr int LASTLOG = REM ? REM : EL;  // log2 radix of the last stage
+    static constexpr int TPT = (L / E) * C;        // threads per tile
     static constexpr int TPC = TPT >= 128 ? 1 : 128 / TPT;  // tiles per CTA
-    static constexpr int RMAX = L >= 16 ? 16 : L;
-    // log2 radix of stage i: as many radix-16 blocks as fit, then the remainder
-    SA_HDC int rlog(int i) { return i < LOGL / 4 ? 4 : LOGL % 4; }
-    // log2 of M_i = L / (R_0 * ... * R_i)
-    SA_HDC int mlog(int i) {
-        int s = 0;
-        for (int j = 0; j <= i; j++) s += rlog(j);
-        return LOGL - s;
-    }
-    SA_HDC size_t smem_bytes() { return NST > 1 ? (size_t)TPC * L * TILE_C * sizeof(fe) : 0; }
+    static constexpr int THREADS = TPT * TPC;
+    SA_HDC size_t smem_bytes() { return NST > 1 ? (size_t)TPC * L * C * sizeof(fe) : 0; }
 };
 
 SA_HDC int tile_bitrev(int i, int r) {
@@ -105,16 +107,20 @@ SA_HD void dft_regs(fe *x, const fe *cst, int cstep) {
     if constexpr (R >= 2) dft_level<R, 2>(x, cst, cstep);
 }
 
-template <int LOGL>
+// position p = (k_0, k_1, ..., k_last), k_0 most significant -> output index
+// k_0 + R_0 k_1 + R_0 R_1 k_2 + ...   (digit reversal of the mixed radix)
+template <int LOGL, int ELOG, int C>
 SA_HD int tile_digit_reverse(int p) {
-    using P = TilePlan<LOGL>;
+    using P = TilePlan<LOGL, ELOG, C>;
     int o = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < P::NST; i++) {
-        const int k = (p >> P::mlog(i)) & ((1 << P::rlog(i)) - 1);
-        o |= k << (LOGL - P::mlog(i) - P::rlog(i));
+        const int rl = (i < P::NFULL) ? P::EL : P::REM;
+        const int ml = (i < P::NFULL) ? LOGL - (i + 1) * P::EL : 0;  // log2 M_i
+        const int k = (p >> ml) & ((1 << rl) - 1);
+        o |= k << (i * P::EL);  // product of the earlier radices = E^i
     }
     return o;
 }
@@ -143,66 +149,100 @@ SA_HD void tile_st(fe *p, const fe &x) {
 #endif
 }
 
-// One register-block stage for thread t (0 <= t < TPT) of one tile.
-//   sm    : this tile's shared rows, L x 8 elements
-//   b,col0: batch item and first column of the tile; valid = tile exists
-template <int LOGL, int ST>
-SA_HD void ntt_tile_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
-    using P = TilePlan<LOGL>;
-    constexpr int RL = P::rlog(ST), R = 1 << RL, ML = P::mlog(ST), M = 1 << ML;
-    constexpr int U = P::E / R;  // units (independent R-point transforms) per thread
-    constexpr bool FIRST = ST == 0, LAST = ST == P::NST - 1;
-    constexpr int WLOG = LOGL - ML - RL;  // log2 of the product of the earlier radices
-    constexpr int CSTEP = P::RMAX / R;
-    const int c = t & (TILE_C - 1), q = t >> 3;
+// A full-radix (E-point) stage that is NOT the last stage: one unit per thread.
+//   ml = log2 M of this stage (run-time, so all such stages share one copy of the code)
+template <int LOGL, int ELOG, int C>
+SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid, bool first,
+                               int ml) {
+    using P = TilePlan<LOGL, ELOG, C>;
+    constexpr int R = P::E;
+    constexpr int CSTEP = 16 / R;  // a non-last stage exists only when L > E >= 8, so cst = w_16^k
+    const int c = t % C, q = t / C;
     const int col = col0 + c;
     const bool active = valid && col < a.ncols;
+    const int M = 1 << ml, wlog = LOGL - ml - P::EL;
+    const int K = q >> ml, m = q & (M - 1);
+    const int row0 = (K << (ml + P::EL)) + m;
+    fe x[R];
+    if (first) {
+        const fe *src = a.in + b * a.in_sb + (long long)col * a.in_sc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
+        for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (long long)(row0 + d * M) * a.in_sr) : fe_zero();
+    } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int d = 0; d < R; d++) x[d] = tile_ld(sm + (row0 + d * M) * C + c);
+    }
+    dft_regs<R>(x, a.cst, CSTEP);
+    // multiply output k by w_{M*R}^(k*m) = w_L^((k*m) << wlog), then park it in row row0 + k*M
+    tile_st(sm + row0 * C + c, x[0]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < R; k++) {
+        const fe w = tile_ldg(a.tw + ((k * m) << wlog));
+        tile_st(sm + (row0 + k * M) * C + c, fe_montmul(x[k], w));
+    }
+}
+
+// The last stage (radix 2^LASTLOG, M = 1): E / R units per thread, output twiddle, global stores.
+template <int LOGL, int ELOG, int C>
+SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
+    using P = TilePlan<LOGL, ELOG, C>;
+    constexpr int R = 1 << P::LASTLOG, U = P::E / R;
+    constexpr bool FIRST = P::NST == 1;
+    constexpr int CSTEP = LOGL >= 4 ? 16 / R : (1 << LOGL) / R;
+    const int c = t % C, q = t / C;
+    const int col = col0 + c;
+    const bool active = valid && col < a.ncols;
+    fe *dst = a.out + b * a.out_sb + (long long)col * a.out_sc;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int s = 0; s < U; s++) {
-        const int u = q * U + s;
-        const int K = u >> ML, m = u & (M - 1);
-        const int row0 = (K << (ML + RL)) + m;
+        const int row0 = (q * U + s) * R;
         fe x[R];
         if (FIRST) {
             const fe *src = a.in + b * a.in_sb + (long long)col * a.in_sc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int d = 0; d < R; d++)
-                x[d] = active ? tile_ld(src + (long long)(row0 + d * M) * a.in_sr) : fe_zero();
+            for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (long long)(row0 + d) * a.in_sr) : fe_zero();
         } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int d = 0; d < R; d++) x[d] = tile_ld(sm + (row0 + d * M) * TILE_C + c);
+            for (int d = 0; d < R; d++) x[d] = tile_ld(sm + (row0 + d) * C + c);
         }
         dft_regs<R>(x, a.cst, CSTEP);
-        if (!LAST) {
-            // multiply output k by w_{M*R}^(k*m) = w_L^((k*m) << WLOG), then park it in row row0 + k*M
-            tile_st(sm + row0 * TILE_C + c, x[0]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int k = 1; k < R; k++) {
-                const fe w = tile_ldg(a.tw + ((k * m) << WLOG));
-                tile_st(sm + (row0 + k * M) * TILE_C + c, fe_montmul(x[k], w));
-            }
-        } else {
-            fe *dst = a.out + b * a.out_sb + (long long)col * a.out_sc;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int k = 0; k < R; k++) {
-                const int o = tile_digit_reverse<LOGL>(row0 + k * M);
-                fe v = x[k];
-                if (a.twb != nullptr && active) v = fe_montmul(v, tile_ldg(a.twb + (long long)o * a.twb_stride + col));
-                if (a.has_scale) v = fe_montmul(v, a.scale);
-                if (active) tile_st(dst + (long long)o * a.out_sr, v);
-            }
+        for (int k = 0; k < R; k++) {
+            const int o = tile_digit_reverse<LOGL, ELOG, C>(row0 + k);
+            fe v = x[k];
+            if (a.twb != nullptr && active) v = fe_montmul(v, tile_ldg(a.twb + (long long)o * a.twb_stride + col));
+            if (a.has_scale) v = fe_montmul(v, a.scale);
+            if (active) tile_st(dst + (long long)o * a.out_sr, v);
         }
     }
 }
+
+// the whole tile for thread t; `sync` is __syncthreads on the device and a no-op marker on
+// the host (the emulator calls the stages phase by phase instead)
+template <int LOGL, int ELOG, int C>
+struct TileStages {
+    using P = TilePlan<LOGL, ELOG, C>;
+    // stage index st < NLOOP -> full stage with ml = LOGL - (st + 1) * EL
+    SA_HD static void full(int st, int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
+        ntt_tile_full_stage<LOGL, ELOG, C>(t, sm, a, b, col0, valid, st == 0, LOGL - (st + 1) * P::EL);
+    }
+    SA_HD static void last(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
+        ntt_tile_last_stage<LOGL, ELOG, C>(t, sm, a, b, col0, valid);
+    }
+};
 
 }  // namespace sa

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -22,6 +23,7 @@
 #include "ntt_tile.cuh"
 
 using namespace sa;
+
 
 // ------------------------------------------------------------------ plumbing --
 static thread_local std::string g_last_error;
@@ -56,27 +58,34 @@ static inline int host_log2(size_t n) {
 }
 
 // ------------------------------------------------------------------- kernels --
-template <int LOGL>
-__global__ void __launch_bounds__(TilePlan<LOGL>::TPT *TilePlan<LOGL>::TPC)
+template <int LOGL, int ELOG, int C>
+struct TileLaunch {
+    using P = TilePlan<LOGL, ELOG, C>;
+    // aim for 1024 resident threads per SM with 8-element blocks (<= 64 registers) and 512 with
+    // 16-element blocks (<= 128 registers)
+    static constexpr int TARGET = (P::EL <= 3 && LOGL > 3) ? 1024 : 512;
+    static constexpr int MINB = TARGET / P::THREADS > 0 ? TARGET / P::THREADS : 1;
+};
+
+template <int LOGL, int ELOG, int C>
+__global__ void __launch_bounds__(TilePlan<LOGL, ELOG, C>::THREADS, TileLaunch<LOGL, ELOG, C>::MINB)
     ntt_tile_kernel(const __grid_constant__ TileArgs a, long long total_tiles, int tiles_per_batch) {
-    using P = TilePlan<LOGL>;
+    using P = TilePlan<LOGL, ELOG, C>;
+    using S = TileStages<LOGL, ELOG, C>;
     extern __shared__ uint4 sa_smem_u4[];
     fe *smem = reinterpret_cast<fe *>(sa_smem_u4);
     const int tic = threadIdx.x / P::TPT, t = threadIdx.x % P::TPT;
     const long long tile = (long long)blockIdx.x * P::TPC + tic;
     const bool valid = tile < total_tiles;
     const long long b = valid ? tile / tiles_per_batch : 0;
-    const int col0 = valid ? (int)(tile % tiles_per_batch) * TILE_C : 0;
-    fe *sm = smem + (size_t)tic * P::L * TILE_C;
-    ntt_tile_stage<LOGL, 0>(t, sm, a, b, col0, valid);
-    if constexpr (P::NST > 1) {
+    const int col0 = valid ? (int)(tile % tiles_per_batch) * C : 0;
+    fe *sm = smem + (size_t)tic * P::L * C;
+#pragma unroll 1
+    for (int st = 0; st < P::NLOOP; st++) {
+        S::full(st, t, sm, a, b, col0, valid);
         __syncthreads();
-        ntt_tile_stage<LOGL, 1>(t, sm, a, b, col0, valid);
     }
-    if constexpr (P::NST > 2) {
-        __syncthreads();
-        ntt_tile_stage<LOGL, 2>(t, sm, a, b, col0, valid);
-    }
+    S::last(t, sm, a, b, col0, valid);
 }
 
 // out[e] = base^e * lead (Montgomery form) for e < count; 16 consecutive powers per thread
@@ -279,6 +288,42 @@ __global__ void k_microbench(fe *sink, int iters) {
     if (acc.v[0] == 0xDEADBEEFu && acc.v[1] == 0x1u) tile_st(sink + t, acc);
 }
 
+// ------------------------------------------------------------- workspaces --
+// Grow-only scratch buffers, one per (device, stream): the four-step NTT needs an n*batch
+// intermediate and allocating it per call (even stream-ordered) costs more than the kernels.
+static std::mutex g_ws_mu;
+static std::map<std::pair<int, cudaStream_t>, std::pair<void *, size_t>> g_ws;
+static int get_workspace(void **out, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    auto &slot = g_ws[std::make_pair(dev, st)];
+    if (slot.second < bytes) {
+        if (slot.first) {
+            SA_CUDA(cudaStreamSynchronize(st));  // earlier work on this stream may still use it
+            SA_CUDA(cudaFree(slot.first));
+            slot.first = nullptr;
+            slot.second = 0;
+        }
+        SA_CUDA(cudaMalloc(&slot.first, bytes));
+        slot.second = bytes;
+    }
+    *out = slot.first;
+    return SA_OK;
+}
+// stream-ordered pool allocations (small flags, host-entry staging) keep their memory cached
+static void keep_pool_memory() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+}
+
 // ---------------------------------------------------------------- NTT plans --
 struct NttPlan {
     int log_n = 0, l1 = 0, l2 = 0;
@@ -351,35 +396,63 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
     return SA_OK;
 }
 
-template <int LOGL>
+template <int LOGL, int ELOG, int C>
 static int launch_tile(const TileArgs &a, cudaStream_t st) {
-    using P = TilePlan<LOGL>;
-    const int tiles_per_batch = (a.ncols + TILE_C - 1) / TILE_C;
+    using P = TilePlan<LOGL, ELOG, C>;
+    const int tiles_per_batch = (a.ncols + C - 1) / C;
     const long long total = (long long)tiles_per_batch * a.nbatch;
     const long long grid = (total + P::TPC - 1) / P::TPC;
     const size_t smem = P::smem_bytes();
     static bool attr_done = false;
     if (smem > 48 * 1024 && !attr_done) {
-        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL, ELOG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
         attr_done = true;
     }
-    ntt_tile_kernel<LOGL><<<(unsigned)grid, P::TPT * P::TPC, smem, st>>>(a, total, tiles_per_batch);
+    ntt_tile_kernel<LOGL, ELOG, C><<<(unsigned)grid, P::THREADS, smem, st>>>(a, total, tiles_per_batch);
     SA_LAUNCH_CHECK();
     return SA_OK;
 }
+
+// tile shape: register block (log2 elements per thread) and columns per tile; with -DSA_TUNE
+// the environment variables SA_NTT_ELOG / SA_NTT_C select a shape for tuning runs.
+static int g_tile_elog = -1, g_tile_c = -1;
+static void tile_config() {
+    if (g_tile_elog >= 0) return;
+    const char *e = getenv("SA_NTT_ELOG"), *c = getenv("SA_NTT_C");
+    g_tile_elog = e ? atoi(e) : 0;
+    g_tile_c = c ? atoi(c) : 0;
+}
+template <int LOGL>
+static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
+    tile_config();
+#ifdef SA_TUNE
+    if (LOGL >= 9 && g_tile_elog > 0) {
+        if (g_tile_elog == 3 && g_tile_c == 8) return launch_tile<LOGL, 3, 8>(a, st);
+        if (g_tile_elog == 3 && g_tile_c == 4) return launch_tile<LOGL, 3, 4>(a, st);
+        if (g_tile_elog == 3 && g_tile_c == 2) return launch_tile<LOGL, 3, 2>(a, st);
+        if (g_tile_elog == 4 && g_tile_c == 4) return launch_tile<LOGL, 4, 4>(a, st);
+        if (g_tile_elog == 4 && g_tile_c == 2) return launch_tile<LOGL, 4, 2>(a, st);
+        if (g_tile_elog == 4 && g_tile_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
+    }
+#endif
+    // measured on B200 (profiles/r01_tile_shapes.md): 8-element register blocks (64 registers,
+    // 32 warps/SM) with 4-column tiles win for the big tiles; small tiles keep 16-element blocks
+    if (LOGL >= 9) return launch_tile<LOGL, 3, 4>(a, st);
+    return launch_tile<LOGL, 4, 8>(a, st);
+}
 static int launch_tile_dyn(int logl, const TileArgs &a, cudaStream_t st) {
     switch (logl) {
-        case 1: return launch_tile<1>(a, st);
-        case 2: return launch_tile<2>(a, st);
-        case 3: return launch_tile<3>(a, st);
-        case 4: return launch_tile<4>(a, st);
-        case 5: return launch_tile<5>(a, st);
-        case 6: return launch_tile<6>(a, st);
-        case 7: return launch_tile<7>(a, st);
-        case 8: return launch_tile<8>(a, st);
-        case 9: return launch_tile<9>(a, st);
-        case 10: return launch_tile<10>(a, st);
+        case 1: return launch_tile_shape<1>(a, st);
+        case 2: return launch_tile_shape<2>(a, st);
+        case 3: return launch_tile_shape<3>(a, st);
+        case 4: return launch_tile_shape<4>(a, st);
+        case 5: return launch_tile_shape<5>(a, st);
+        case 6: return launch_tile_shape<6>(a, st);
+        case 7: return launch_tile_shape<7>(a, st);
+        case 8: return launch_tile_shape<8>(a, st);
+        case 9: return launch_tile_shape<9>(a, st);
+        case 10: return launch_tile_shape<10>(a, st);
     }
     return SA_ESIZE;
 }
@@ -418,14 +491,13 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     shape.l1 = p->l1;
     shape.l2 = p->l2;
     fe *tmp = nullptr;
-    SA_CUDA(cudaMallocAsync((void **)&tmp, sizeof(fe) * n * batch, st));
+    if ((rc = get_workspace((void **)&tmp, sizeof(fe) * n * batch, st)) != SA_OK) return rc;
     ntt_fill_pass1(a, (const fe *)in, tmp, shape, batch, p->tw1, p->twb, p->cst1);
     rc = launch_tile_dyn(p->l1, a, st);
     if (rc == SA_OK) {
         ntt_fill_pass2(a, tmp, (fe *)out, shape, batch, p->tw2, p->cst2);
         rc = launch_tile_dyn(p->l2, a, st);
     }
-    cudaFreeAsync(tmp, st);
     return rc;
 }
 
@@ -436,6 +508,7 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     const size_t bytes = (size_t(16) << log_n) * batch;
     if (bytes == 0) return SA_OK;
     void *dev = nullptr;
+    keep_pool_memory();
     SA_CUDA(cudaMallocAsync(&dev, bytes, st));
     SA_CUDA(cudaMemcpyAsync(dev, in_host, bytes, cudaMemcpyHostToDevice, st));
     int rc = sa_ntt(dev, dev, log_n, root, inverse, batch, stream);
@@ -464,6 +537,7 @@ int sa_pointwise_div(void *out, const void *a, const void *b, size_t n, void *st
     if (n == 0) return SA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int *flag = nullptr;
+    keep_pool_memory();
     SA_CUDA(cudaMallocAsync((void **)&flag, sizeof(int), st));
     SA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     k_pointwise_div<<<grid_for(((long long)n + 7) / 8, 128), 128, 0, st>>>((fe *)out, (const fe *)a,
@@ -533,6 +607,7 @@ int sa_merkle_open(void *paths_out, const void *tree, size_t n, const uint64_t *
     if (k == 0 || depth == 0) return SA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     uint64_t *idx = nullptr;
+    keep_pool_memory();
     SA_CUDA(cudaMallocAsync((void **)&idx, 8 * k, st));
     SA_CUDA(cudaMemcpyAsync(idx, indices_host, 8 * k, cudaMemcpyHostToDevice, st));
     const long long total = (long long)k * depth * 8;
@@ -550,6 +625,7 @@ int sa_gather(void *out, const void *values, size_t n, const uint64_t *indices_h
     if (k == 0) return SA_OK;
     cudaStream_t st = (cudaStream_t)stream;
     uint64_t *idx = nullptr;
+    keep_pool_memory();
     SA_CUDA(cudaMallocAsync((void **)&idx, 8 * k, st));
     SA_CUDA(cudaMemcpyAsync(idx, indices_host, 8 * k, cudaMemcpyHostToDevice, st));
     k_gather<<<(unsigned)((k + 127) / 128), 128, 0, st>>>((fe *)out, (const fe *)values, idx, (long long)k);

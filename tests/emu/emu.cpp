@@ -22,35 +22,45 @@ static fe from_limbs(const uint64_t x[2]) {
     return fe_make((uint32_t)x[0], (uint32_t)(x[0] >> 32), (uint32_t)x[1], (uint32_t)(x[1] >> 32));
 }
 
-template <int LOGL>
+static int g_elog = 4, g_c = 8;  // tile shape under test (emu_set_shape)
+
+template <int LOGL, int ELOG, int C>
 static void run_tiles(const TileArgs &a) {
-    using P = TilePlan<LOGL>;
-    const int tiles_per_batch = (a.ncols + TILE_C - 1) / TILE_C;
+    using P = TilePlan<LOGL, ELOG, C>;
+    using S = TileStages<LOGL, ELOG, C>;
+    const int tiles_per_batch = (a.ncols + C - 1) / C;
     const long long total = (long long)tiles_per_batch * a.nbatch;
-    std::vector<fe> sm((size_t)P::L * TILE_C);
+    std::vector<fe> sm((size_t)P::L * C);
     for (long long tile = 0; tile < total; tile++) {
         const long long b = tile / tiles_per_batch;
-        const int col0 = (int)(tile % tiles_per_batch) * TILE_C;
+        const int col0 = (int)(tile % tiles_per_batch) * C;
         // each loop over t is one barrier phase of the CTA
-        for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 0>(t, sm.data(), a, b, col0, true);
-        if constexpr (P::NST > 1)
-            for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 1>(t, sm.data(), a, b, col0, true);
-        if constexpr (P::NST > 2)
-            for (int t = 0; t < P::TPT; t++) ntt_tile_stage<LOGL, 2>(t, sm.data(), a, b, col0, true);
+        for (int st = 0; st < P::NLOOP; st++)
+            for (int t = 0; t < P::TPT; t++) S::full(st, t, sm.data(), a, b, col0, true);
+        for (int t = 0; t < P::TPT; t++) S::last(t, sm.data(), a, b, col0, true);
     }
+}
+template <int LOGL>
+static void run_tiles_shape(const TileArgs &a) {
+    if (g_elog == 3 && g_c == 8) return run_tiles<LOGL, 3, 8>(a);
+    if (g_elog == 3 && g_c == 4) return run_tiles<LOGL, 3, 4>(a);
+    if (g_elog == 3 && g_c == 2) return run_tiles<LOGL, 3, 2>(a);
+    if (g_elog == 4 && g_c == 4) return run_tiles<LOGL, 4, 4>(a);
+    if (g_elog == 4 && g_c == 2) return run_tiles<LOGL, 4, 2>(a);
+    return run_tiles<LOGL, 4, 8>(a);
 }
 static void run_tiles_dyn(int logl, const TileArgs &a) {
     switch (logl) {
-        case 1: run_tiles<1>(a); break;
-        case 2: run_tiles<2>(a); break;
-        case 3: run_tiles<3>(a); break;
-        case 4: run_tiles<4>(a); break;
-        case 5: run_tiles<5>(a); break;
-        case 6: run_tiles<6>(a); break;
-        case 7: run_tiles<7>(a); break;
-        case 8: run_tiles<8>(a); break;
-        case 9: run_tiles<9>(a); break;
-        case 10: run_tiles<10>(a); break;
+        case 1: run_tiles_shape<1>(a); break;
+        case 2: run_tiles_shape<2>(a); break;
+        case 3: run_tiles_shape<3>(a); break;
+        case 4: run_tiles_shape<4>(a); break;
+        case 5: run_tiles_shape<5>(a); break;
+        case 6: run_tiles_shape<6>(a); break;
+        case 7: run_tiles_shape<7>(a); break;
+        case 8: run_tiles_shape<8>(a); break;
+        case 9: run_tiles_shape<9>(a); break;
+        case 10: run_tiles_shape<10>(a); break;
     }
 }
 static std::vector<fe> pow_table(const fe &base_m, const fe &lead_m, size_t count) {
@@ -64,6 +74,11 @@ static std::vector<fe> pow_table(const fe &base_m, const fe &lead_m, size_t coun
 }
 
 extern "C" {
+
+void emu_set_shape(int elog, int c) {
+    g_elog = elog;
+    g_c = c;
+}
 
 void emu_montmul(uint64_t *out, const uint64_t *a, const uint64_t *b) {
     fe r = fe_montmul_portable(from_limbs(a), from_limbs(b));

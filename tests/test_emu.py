@@ -44,8 +44,10 @@ def test_portable_field(E):
         assert (int(out[0]) | (int(out[1]) << 64)) == O.inverse(a)
 
 
+@pytest.mark.parametrize("shape", [(4, 8), (4, 4), (4, 2), (3, 8), (3, 4), (3, 2)])
 @pytest.mark.parametrize("logn", list(range(0, 14)))
-def test_tile_ntt_all_sizes(E, logn):
+def test_tile_ntt_all_sizes(E, logn, shape):
+    E.emu_set_shape(*shape)
     rng = random.Random(100 + logn)
     n = 1 << logn
     w = O.primitive_nth_root(n)
@@ -63,6 +65,7 @@ def test_tile_ntt_all_sizes(E, logn):
 
 
 def test_tile_ntt_2_16_and_nonstandard_root(E):
+    E.emu_set_shape(4, 8)
     rng = random.Random(9)
     n = 1 << 16
     w = pow(O.primitive_nth_root(n), 12345, P)  # another primitive root
