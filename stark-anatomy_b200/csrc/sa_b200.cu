@@ -292,12 +292,12 @@ __global__ void k_microbench(fe *sink, int iters) {
 // Grow-only scratch buffers, one per (device, stream): the four-step NTT needs an n*batch
 // intermediate and allocating it per call (even stream-ordered) costs more than the kernels.
 static std::mutex g_ws_mu;
-static std::map<std::pair<int, cudaStream_t>, std::pair<void *, size_t>> g_ws;
-static int get_workspace(void **out, size_t bytes, cudaStream_t st) {
+static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void *, size_t>> g_ws;
+static int get_workspace(void **out, size_t bytes, cudaStream_t st, int tag = 0) {
     int dev = 0;
     SA_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_ws_mu);
-    auto &slot = g_ws[std::make_pair(dev, st)];
+    auto &slot = g_ws[std::make_tuple(dev, st, tag)];
     if (slot.second < bytes) {
         if (slot.first) {
             SA_CUDA(cudaStreamSynchronize(st));  // earlier work on this stream may still use it
@@ -501,19 +501,65 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     return rc;
 }
 
+// Host entry: H2D, transforms, D2H.  Batches are cut into per-transform chunks that rotate over
+// three internal streams so that the upload of chunk i+1, the kernels of chunk i and the download
+// of chunk i-1 overlap (PCIe is full duplex); with pinned host buffers the call is bound by the
+// slower copy direction instead of the sum of both.
+static cudaStream_t g_copy_streams[3];
+static cudaEvent_t g_copy_events[4];
+static int copy_streams_ready() {
+    static bool ready = false;
+    if (ready) return SA_OK;
+    for (int i = 0; i < 3; i++) SA_CUDA(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) SA_CUDA(cudaEventCreateWithFlags(&g_copy_events[i], cudaEventDisableTiming));
+    ready = true;
+    return SA_OK;
+}
+
 int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,
                 size_t batch, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (log_n < 0 || log_n > 20) return SA_ESIZE;
-    const size_t bytes = (size_t(16) << log_n) * batch;
+    const size_t one = size_t(16) << log_n;
+    const size_t bytes = one * batch;
     if (bytes == 0) return SA_OK;
-    void *dev = nullptr;
-    keep_pool_memory();
-    SA_CUDA(cudaMallocAsync(&dev, bytes, st));
-    SA_CUDA(cudaMemcpyAsync(dev, in_host, bytes, cudaMemcpyHostToDevice, st));
-    int rc = sa_ntt(dev, dev, log_n, root, inverse, batch, stream);
-    if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(out_host, dev, bytes, cudaMemcpyDeviceToHost, st));
-    cudaFreeAsync(dev, st);
+    int rc;
+    // chunk = as many transforms as fit ~16 MiB (one 2^20 transform); small jobs stay on `st`
+    size_t per_chunk = one >= (size_t(16) << 20) ? 1 : (size_t(16) << 20) / one;
+    if (per_chunk > batch) per_chunk = batch;
+    const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
+    if (nchunks < 2) {
+        void *dev = nullptr;
+        if ((rc = get_workspace(&dev, bytes, st, 1)) != SA_OK) return rc;
+        SA_CUDA(cudaMemcpyAsync(dev, in_host, bytes, cudaMemcpyHostToDevice, st));
+        rc = sa_ntt(dev, dev, log_n, root, inverse, batch, stream);
+        if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(out_host, dev, bytes, cudaMemcpyDeviceToHost, st));
+        SA_CUDA(cudaStreamSynchronize(st));
+        return rc;
+    }
+    if ((rc = copy_streams_ready()) != SA_OK) return rc;
+    // two device buffers per copy stream (the D2H of chunk c must not race the H2D of chunk c+3)
+    void *buf[3][2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 2; j++)
+            if ((rc = get_workspace(&buf[i][j], per_chunk * one, g_copy_streams[i], 1 + j)) != SA_OK) return rc;
+    SA_CUDA(cudaEventRecord(g_copy_events[3], st));
+    for (int i = 0; i < 3; i++) SA_CUDA(cudaStreamWaitEvent(g_copy_streams[i], g_copy_events[3], 0));
+    rc = SA_OK;
+    for (size_t c = 0; c < nchunks && rc == SA_OK; c++) {
+        const int si = (int)(c % 3), bi = (int)((c / 3) % 2);
+        cudaStream_t cs = g_copy_streams[si];
+        const size_t first = c * per_chunk, cnt = (first + per_chunk <= batch) ? per_chunk : batch - first;
+        const char *src = (const char *)in_host + first * one;
+        char *dst = (char *)out_host + first * one;
+        SA_CUDA(cudaMemcpyAsync(buf[si][bi], src, cnt * one, cudaMemcpyHostToDevice, cs));
+        rc = sa_ntt(buf[si][bi], buf[si][bi], log_n, root, inverse, cnt, (void *)cs);
+        if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(dst, buf[si][bi], cnt * one, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int i = 0; i < 3; i++) {
+        SA_CUDA(cudaEventRecord(g_copy_events[i], g_copy_streams[i]));
+        SA_CUDA(cudaStreamWaitEvent(st, g_copy_events[i], 0));
+    }
     SA_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
