@@ -93,6 +93,7 @@ def cpu_arm(steps, warmup, batch):
     x = np.stack([rng.integers(0, 1 << 64, size=(batch, N), dtype=np.uint64),
                   rng.integers(0, 0xCB80000000000000, size=(batch, N), dtype=np.uint64)], axis=2)
     w = O.primitive_nth_root(N)
+    O.lib().so_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use the whole host
     threads = O.lib().so_num_threads()
     for _ in range(warmup):
         O.ntt_batch_np(w, x)
@@ -137,6 +138,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = sa_engine.get_engine()
@@ -239,16 +241,12 @@ def run_ours(args):
         rounds = O.fri_num_rounds(N, 4, 64)
 
         def fri_commit():
-            objs, vec = [], cw
-            omega, off = omega0, off0
-            tree = eng.merkle_tree(vec)
-            for r in range(rounds):
-                objs.append(eng.tree_root(tree))
-                if r == rounds - 1:
-                    break
-                alpha = O.sample(hashlib.shake_256(pickle.dumps(objs)).digest(32))
-                vec, tree = eng.fri_round(vec, alpha, off, omega)
-                omega, off = omega * omega % O.P, off * off % O.P
+            objs = []
+
+            def on_root(r, root, want_alpha):  # the host side of fri.py:71-79 on a plain ProofStream
+                objs.append(root)
+                return O.sample(hashlib.shake_256(pickle.dumps(objs)).digest(32)) if want_alpha else None
+            eng.fri_commit(cw, rounds, off0, omega0, on_root)
             return objs
         fri_commit()
         torch.cuda.synchronize()
@@ -267,8 +265,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline on this box's host cores, bounded sample (~10-20 s)
-    cpu_value, cpu_threads, cpu_dt = cpu_arm(2, 1, BATCH)
+    # ---- CPU baseline on this box's host cores, bounded sample (a few seconds); N = 1 only
+    cpu_value = cpu_threads = None
+    if world == 1:
+        cpu_value, cpu_threads, cpu_dt = cpu_arm(2, 1, BATCH)
 
     # roofline of the dominant kernel, ntt_tile_kernel<10>: two launches per step (column pass, row pass);
     # each launch reads and writes the whole batch once: 32 * n * BATCH algorithmic bytes

@@ -39,7 +39,8 @@ enum {
     SA_ENOTPRIM = -3,   /* ntt.py:11  "primitive root is not primitive nth root of unity, ..." */
     SA_EDIVZERO = -4,   /* algebra.py:92 "divide by zero" (element-wise division, ntt.py:172) */
     SA_EINDEX = -5,     /* merkle.py:18 "cannot open invalid index" */
-    SA_ESIZE = -6,      /* unsupported size (log_n > 30, n == 0, ...) */
+    SA_ESIZE = -6,      /* unsupported size (log_n > 20, n == 0, ...) */
+    SA_ECALLBACK = -7,  /* the challenge callback of sa_fri_commit returned non-zero */
     SA_ECUDA = -100     /* CUDA runtime error; sa_last_error() has the text */
 };
 
@@ -97,6 +98,24 @@ int sa_fri_fold(void *next, const void *cw, size_t n, const uint64_t alpha[2], c
                 const uint64_t omega[2], void *stream);
 int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const uint64_t alpha[2],
                  const uint64_t offset[2], const uint64_t omega[2], void *stream);
+
+/* ---- code/fri.py:56-96 Fri.commit, the whole round loop in one call -----------------------
+ * Round 0 builds the Merkle tree of `codeword` (n = 2^k elements); every later round is the
+ * fused fold + tree kernel on the previous layer.  After each round the 64-byte root is copied
+ * to the host and `challenge(user, round, root, alpha_out, want_alpha)` is called: the caller
+ * pushes the root into its proof stream (fri.py:72) and, when want_alpha != 0, writes the
+ * Fiat-Shamir challenge alpha = field.sample(proof_stream.prover_fiat_shamir()) (fri.py:79)
+ * into alpha_out; a non-zero return aborts the commit (SA_ECALLBACK).  omega / offset are
+ * squared per round (fri.py:87-88).
+ *   layers : device buffer for layers 1 .. rounds-1, layer r (n >> r elements) at element
+ *            offset n - (n >> (r-1)), i.e. back to back;  total n - (n >> (rounds-1)) elements
+ *   trees  : device buffer for the trees of layers 0 .. rounds-1, back to back, tree r has
+ *            2 * (n >> r) nodes of 64 bytes;  total 4n - (4n >> rounds) nodes               */
+typedef int (*sa_fri_challenge_fn)(void *user, int round, const uint8_t root[64], uint64_t alpha_out[2],
+                                   int want_alpha);
+int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int rounds,
+                  const uint64_t offset[2], const uint64_t omega[2], sa_fri_challenge_fn challenge, void *user,
+                  void *stream);
 
 /* ---- self checks (used by tests / smoke) ------------------------------------------------
  * Runs the sm_100a carry-chain field arithmetic against the portable C++ version on

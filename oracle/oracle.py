@@ -45,6 +45,8 @@ def lib():
         vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
         L.so_init.restype = None
         L.so_num_threads.restype = ci
+        L.so_set_threads.argtypes = [ci]
+        L.so_set_threads.restype = None
         for name in ("so_fe_mul", "so_fe_add", "so_fe_sub", "so_fe_pow"):
             getattr(L, name).argtypes = [vp, vp, vp]
             getattr(L, name).restype = None

@@ -746,6 +746,61 @@ int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const ui
     return merkle_reduce(a, st);
 }
 
+int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int rounds,
+                  const uint64_t offset[2], const uint64_t omega[2], sa_fri_challenge_fn challenge, void *user,
+                  void *stream) {
+    if (!host_is_pow2(n) || rounds < 1 || (n >> (rounds - 1)) < 1) return SA_ESIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    static uint8_t *root_pinned = nullptr;  // 64-byte landing pad for the per-round root
+    if (!root_pinned) SA_CUDA(cudaHostAlloc((void **)&root_pinned, 64, cudaHostAllocDefault));
+    fe off = fe_from_limbs(offset), om = fe_from_limbs(omega);
+    const fe *cur = (const fe *)codeword;
+    fe *layer_out = (fe *)layers;
+    uint8_t *tree = (uint8_t *)trees;
+    size_t len = n;
+    int rc;
+    for (int r = 0; r < rounds; r++) {
+        if (r == 0) {
+            MerkleArgs a;
+            memset(&a, 0, sizeof(a));
+            a.tree = (uint64_t *)tree;
+            a.width = (long long)len;
+            a.mode = 1;
+            a.values = cur;
+            if ((rc = merkle_reduce(a, st)) != SA_OK) return rc;
+        }
+        SA_CUDA(cudaMemcpyAsync(root_pinned, tree + 64, 64, cudaMemcpyDeviceToHost, st));
+        SA_CUDA(cudaStreamSynchronize(st));
+        uint64_t alpha[2] = {0, 0};
+        const int want = r != rounds - 1;
+        if (challenge(user, r, root_pinned, alpha, want) != 0) return SA_ECALLBACK;
+        if (!want) break;
+        // fold layer r into layer r+1 and build its tree, one fused kernel (+ upper-level launches)
+        fe *xinv = nullptr;
+        const uint64_t off_l[2] = {(uint64_t)off.v[0] | ((uint64_t)off.v[1] << 32), (uint64_t)off.v[2] | ((uint64_t)off.v[3] << 32)};
+        if ((rc = get_xinv(&xinv, om, len, st)) != SA_OK) return rc;
+        uint8_t *next_tree = tree + 128 * len;  // this tree has 2 * len nodes of 64 bytes
+        MerkleArgs a;
+        memset(&a, 0, sizeof(a));
+        a.tree = (uint64_t *)next_tree;
+        a.width = (long long)(len / 2);
+        a.mode = 2;
+        a.prev = cur;
+        a.next = layer_out;
+        a.xinv = xinv;
+        fri_scalars(&a.s_m, &a.inv2_m, alpha, off_l);
+        if ((rc = merkle_reduce(a, st)) != SA_OK) return rc;
+        cur = layer_out;
+        layer_out += len / 2;
+        tree = next_tree;
+        len /= 2;
+        const fe om_m = fe_to_mont(om), off_m = fe_to_mont(off);
+        om = fe_montmul(om_m, om);      // omega^2  (Montgomery form times canonical = canonical product)
+        off = fe_montmul(off_m, off);   // offset^2
+    }
+    return SA_OK;
+}
+
 long long sa_selftest_field(size_t count, uint64_t seed) {
     unsigned long long *d = nullptr, h = 0;
     SA_CUDA(cudaMalloc(&d, 8));

@@ -141,41 +141,36 @@ class Fri:
         eng = sa_engine.get_engine()
         p = self.field.p
         omega, offset = self.omega.value, self.offset.value
-        codewords = []
-        self._resident = {}
         rounds = self.num_rounds()
+        self._resident = {}
+        N = len(codeword)
+        # make sure omega has the right order (fri.py:68; if it holds for round 0 it holds for
+        # every squared omega / halved length after it)
+        assert(pow(omega, N - 1, p) == pow(omega, -1, p)), "error in commit: omega does not have the right order!"
 
-        current = codeword  # what the reference would hold in `codeword`
-        vec = eng.upload(sa_marshal.pack(codeword))
-        tree = eng.merkle_tree(vec)  # round 0: leaf hashing + tree, no fold
+        def on_root(r, root, want_alpha):
+            # compute and send Merkle root (fri.py:71-72); get challenge (fri.py:79)
+            proof_stream.push(root)
+            if want_alpha:
+                return self.field.sample(proof_stream.prover_fiat_shamir()).value
+            return None
 
-        for r in range(rounds):
-            N = len(current)
-            # make sure omega has the right order
-            assert(pow(omega, N - 1, p) == pow(omega, -1, p)), "error in commit: omega does not have the right order!"
-            # compute and send Merkle root
-            proof_stream.push(eng.tree_root(tree))
-            # prepare next round, but only if necessary
-            if r == rounds - 1:
-                break
-            # get challenge
-            alpha = self.field.sample(proof_stream.prover_fiat_shamir())
-            # collect codeword
-            codewords += [current]
-            if not isinstance(current, DeviceCodeword):
-                self._resident[id(current)] = (current, vec, tree)
-            # split and fold (fri.py:85) fused with the next round's leaf hashing and tree
-            vec, tree = eng.fri_round(vec, alpha.value, offset, omega)
-            current = DeviceCodeword(vec, tree, self.field, N // 2)
-            omega = omega * omega % p
-            offset = offset * offset % p
+        # the whole ladder runs on the device: round 0 = leaf hashing + tree, every later round =
+        # one fused kernel (split-and-fold fri.py:85 + leaf hashing + tree); only the 64-byte roots
+        # come back, through on_root
+        vecs, trees = eng.fri_commit(eng.upload(sa_marshal.pack(codeword)), rounds, offset, omega, on_root)
 
+        codewords = [codeword]
+        self._resident[id(codeword)] = (codeword, vecs[0], trees[0])
+        for r in range(1, rounds):
+            codewords.append(DeviceCodeword(vecs[r], trees[r], self.field, N >> r))
         # send last codeword (a real list: it is pickled into the transcript)
-        last = current if not isinstance(current, DeviceCodeword) else current.tolist()
+        last = codewords[-1]
+        if isinstance(last, DeviceCodeword):
+            last = last.tolist()
+            codewords[-1] = last
         proof_stream.push(last)
-        self._resident[id(last)] = (last, vec, tree)
-        # collect last codeword too
-        codewords = codewords + [last]
+        self._resident[id(last)] = (last, vecs[-1], trees[-1])
         return codewords
 
     # ---------------------------------------------------------------- query --

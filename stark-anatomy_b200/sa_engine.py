@@ -25,6 +25,8 @@ SA_ERRORS = {
     -5: "cannot open invalid index",                                                         # merkle.py:18
     -6: "unsupported size",
 }
+FRI_CHALLENGE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.POINTER(ctypes.c_uint64), ctypes.c_int)
 
 # every symbol include/sa_b200.h declares: (name, restype, argtypes)
 _vp, _sz, _ci, _u64p = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)
@@ -43,6 +45,7 @@ SYMBOLS = [
     ("sa_gather", _ci, [_vp, _vp, _sz, _u64p, _sz, _vp]),
     ("sa_fri_fold", _ci, [_vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
     ("sa_fri_round", _ci, [_vp, _vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
+    ("sa_fri_commit", _ci, [_vp, _vp, _vp, _sz, _ci, _u64p, _u64p, _vp, _vp, _vp]),
     ("sa_selftest_field", ctypes.c_longlong, [_sz, ctypes.c_uint64]),
     ("sa_microbench", ctypes.c_double, [_ci, _ci, _ci, _ci, _ci]),
 ]
@@ -93,6 +96,8 @@ class CudaEngine:
             return
         if rc in SA_ERRORS:
             raise SaError(SA_ERRORS[rc])
+        if rc == -7:
+            raise RuntimeError("sa_b200: the challenge callback failed")
         raise RuntimeError("sa_b200: CUDA error: %s" % self.lib.sa_last_error().decode())
 
     def empty(self, n):
@@ -228,6 +233,45 @@ class CudaEngine:
         self._check(self.lib.sa_fri_round(out.data_ptr(), tree.data_ptr(), vec.data_ptr(), n, _limbs(alpha),
                                           _limbs(offset), _limbs(omega), self._stream()))
         return out, tree
+
+    def fri_commit(self, vec, rounds, offset, omega, on_root):
+        """code/fri.py:56-96 round loop in one C call (sa_fri_commit).
+
+        on_root(round, root_bytes, want_alpha) is called after every round with the 64-byte
+        Merkle root; it returns the challenge alpha (int) when want_alpha.  Returns
+        (layers, trees): device vectors / trees of layers 0 .. rounds-1 (layer 0 is `vec`)."""
+        vec = vec.contiguous()
+        n = vec.shape[0]
+        layers = self.empty(max(n - (n >> (rounds - 1)), 1))
+        trees = self.torch.empty((4 * n - ((4 * n) >> rounds), 64), dtype=self.torch.uint8, device=self.device)
+        errors = []
+
+        def challenge(_user, r, root_ptr, alpha_out, want):
+            try:
+                alpha = on_root(r, ctypes.string_at(root_ptr, 64), bool(want))
+                if want:
+                    alpha_out[0] = alpha & 0xFFFFFFFFFFFFFFFF
+                    alpha_out[1] = alpha >> 64
+                return 0
+            except BaseException as exc:  # re-raised below, outside the C frame
+                errors.append(exc)
+                return 1
+        cb = FRI_CHALLENGE_FN(challenge)
+        rc = self.lib.sa_fri_commit(layers.data_ptr(), trees.data_ptr(), vec.data_ptr(), n, rounds, _limbs(offset),
+                                    _limbs(omega), cb, None, self._stream())
+        if errors:
+            raise errors[0]
+        self._check(rc)
+        out_layers, out_trees = [vec], []
+        lo, to, ln = 0, 0, n
+        for r in range(rounds):
+            out_trees.append(trees[to:to + 2 * ln])
+            to += 2 * ln
+            if r + 1 < rounds:
+                out_layers.append(layers[lo:lo + ln // 2])
+                lo += ln // 2
+                ln //= 2
+        return out_layers, out_trees
 
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)

@@ -108,6 +108,22 @@ class OracleEngine:
         nxt = O.fri_fold_np(vec, alpha, offset, omega)
         return nxt, O.merkle_tree_np(nxt)
 
+    def fri_commit(self, vec, rounds, offset, omega, on_root):
+        self._log("fri_commit", vec.shape[0], rounds)
+        layers, trees = [vec], []
+        cur = vec
+        for r in range(rounds):
+            tree = O.merkle_tree_np(cur)
+            trees.append(tree)
+            want = r != rounds - 1
+            alpha = on_root(r, tree[1].tobytes(), want)
+            if not want:
+                break
+            cur = O.fri_fold_np(cur, alpha, offset, omega)
+            layers.append(cur)
+            omega, offset = omega * omega % O.P, offset * offset % O.P
+        return layers, trees
+
     def synchronize(self):
         pass
 
