@@ -76,6 +76,14 @@ int sa_scale(void *out, const void *in, size_t n, const uint64_t factor[2], void
 int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
                  void *stream);
 
+/* code/ntt.py:66-80 fast_zerofier: out[0..k] = coefficients of prod_i (X - domain[i]) (monic,
+ * k + 1 coefficients).  k <= 4096 per call (larger domains: split and fast_multiply).       */
+int sa_zerofier(void *out, const void *domain, size_t k, void *stream);
+/* code/ntt.py:102-130 fast_interpolate: out[0..k) = coefficients of the polynomial of degree
+ * < k with value values[i] at domain[i].  SA_EDIVZERO when two domain points coincide (the
+ * reference's element-wise division asserts there).  k <= 4096; synchronises.               */
+int sa_interpolate(void *out, const void *domain, const void *values, size_t k, void *stream);
+
 /* ---- code/merkle.py:6-14 Merkle.commit -------------------------------------------------
  * Builds the whole blake2b-512 tree over n = 2^k leaves, leaf = H(decimal ASCII of the
  * value), node = H(left || right).  `tree` receives 2n nodes of 64 bytes in heap order:

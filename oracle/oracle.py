@@ -63,6 +63,9 @@ def lib():
         L.so_scale.argtypes = [vp, vp, sz, vp]
         L.so_poly_eval.argtypes = [vp, vp, sz, vp, sz]
         L.so_fri_fold.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.so_zerofier.argtypes = [vp, vp, sz]
+        L.so_interpolate.argtypes = [vp, vp, vp, sz]
+        L.so_interpolate.restype = ci
         L.so_blake2b.argtypes = [vp, vp, sz]
         L.so_decimal.argtypes = [vp, vp]
         L.so_decimal.restype = sz
@@ -210,6 +213,24 @@ def poly_eval_np(coeffs, points):
     points = np.ascontiguousarray(points, dtype=np.uint64)
     out = np.empty_like(points)
     lib().so_poly_eval(_ptr(out), _ptr(coeffs), coeffs.shape[0], _ptr(points), points.shape[0])
+    return out
+
+
+def zerofier_np(domain):
+    """ntt.py:66-80: k+1 coefficients of prod (X - d)"""
+    domain = np.ascontiguousarray(domain, dtype=np.uint64)
+    out = np.empty((domain.shape[0] + 1, 2), dtype=np.uint64)
+    lib().so_zerofier(_ptr(out), _ptr(domain), domain.shape[0])
+    return out
+
+
+def interpolate_np(domain, values):
+    """ntt.py:102-130: k coefficients of the interpolant"""
+    domain = np.ascontiguousarray(domain, dtype=np.uint64)
+    values = np.ascontiguousarray(values, dtype=np.uint64)
+    out = np.empty_like(domain)
+    rc = lib().so_interpolate(_ptr(out), _ptr(domain), _ptr(values), domain.shape[0])
+    assert rc == 0, _ERR[rc]
     return out
 
 

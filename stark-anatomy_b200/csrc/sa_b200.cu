@@ -168,6 +168,81 @@ __global__ void k_poly_eval(fe *out, const fe *coeffs, long long ncoef, const fe
     for (long long i = ncoef - 1; i >= 0; i--) acc = fe_add(fe_montmul(acc, x_m), tile_ldg(coeffs + i));
     tile_st(out + j, acc);
 }
+// prod (X - d_i): one CTA, coefficients in shared memory, one sweep per domain point
+constexpr int ZF_THREADS = 1024, ZF_MAXK = 4096, ZF_PER = (ZF_MAXK + 1 + ZF_THREADS - 1) / ZF_THREADS;
+__global__ void __launch_bounds__(ZF_THREADS) k_zerofier(fe *out, const fe *domain, int k) {
+    extern __shared__ uint4 sa_smem_u4[];
+    fe *c = reinterpret_cast<fe *>(sa_smem_u4);
+    fe *dm = c + (k + 1);
+    const int tid = threadIdx.x;
+    for (int j = tid; j <= k; j += ZF_THREADS) c[j] = (j == 0) ? fe_one() : fe_zero();
+    for (int j = tid; j < k; j += ZF_THREADS) dm[j] = fe_to_mont(tile_ld(domain + j));
+    __syncthreads();
+    for (int i = 0; i < k; i++) {
+        const fe d = dm[i];
+        fe val[ZF_PER];
+#pragma unroll
+        for (int s = 0; s < ZF_PER; s++) {
+            const int j = tid + s * ZF_THREADS;
+            if (j <= i + 1) {  // new[j] = old[j-1] - d * old[j]
+                const fe lower = j ? c[j - 1] : fe_zero();
+                const fe cur = (j <= i) ? c[j] : fe_zero();
+                val[s] = fe_sub(lower, fe_montmul(cur, d));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < ZF_PER; s++) {
+            const int j = tid + s * ZF_THREADS;
+            if (j <= i + 1) c[j] = val[s];
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j <= k; j += ZF_THREADS) tile_st(out + j, c[j]);
+}
+// Lagrange interpolation pieces.  q_i = z / (X - d_i) by synthetic division (descending m):
+//   q_i[m-1] = z[m] + d_i * q_i[m];  D_i = q_i(d_i) = z'(d_i);  weight w_i = v_i / D_i
+__global__ void k_interp_weights(fe *w_m, const fe *domain, const fe *values, const fe *z, int k, int *zero_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const fe d = fe_to_mont(tile_ld(domain + i));
+    fe carry = fe_zero(), denom = fe_zero();
+    for (int m = k; m > 0; m--) {
+        carry = fe_add(tile_ldg(z + m), fe_montmul(carry, d));
+        denom = fe_add(fe_montmul(denom, d), carry);
+    }
+    if (fe_is_zero(denom)) {
+        *zero_flag = 1;
+        denom = fe_one();
+    }
+    tile_st(w_m + i, fe_montmul(fe_to_mont(tile_ld(values + i)), fe_mont_inv(fe_to_mont(denom))));
+}
+// QT[m][i] = w_i * q_i[m]  (coalesced over i)
+__global__ void k_interp_rows(fe *QT, const fe *domain, const fe *w_m, const fe *z, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const fe d = fe_to_mont(tile_ld(domain + i)), w = tile_ld(w_m + i);
+    fe carry = fe_zero();
+    for (int m = k; m > 0; m--) {
+        carry = fe_add(tile_ldg(z + m), fe_montmul(carry, d));
+        tile_st(QT + (size_t)(m - 1) * k + i, fe_montmul(carry, w));
+    }
+}
+// out[m] = sum_i QT[m][i]; one CTA per coefficient
+__global__ void __launch_bounds__(256) k_interp_colsum(fe *out, const fe *QT, int k) {
+    __shared__ uint4 red_u4[256];
+    fe *red = reinterpret_cast<fe *>(red_u4);
+    const int m = blockIdx.x, tid = threadIdx.x;
+    fe acc = fe_zero();
+    for (int i = tid; i < k; i += 256) acc = fe_add(acc, tile_ld(QT + (size_t)m * k + i));
+    red[tid] = acc;
+    __syncthreads();
+    for (int w = 128; w >= 1; w >>= 1) {
+        if (tid < w) red[tid] = fe_add(red[tid], red[tid + w]);
+        __syncthreads();
+    }
+    if (tid == 0) tile_st(out + m, red[0]);
+}
 __global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xinv, fe s_m, fe inv2_m) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
@@ -615,6 +690,52 @@ int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points
         (fe *)out, (const fe *)coeffs, (long long)ncoef, (const fe *)points, (long long)npoints);
     SA_LAUNCH_CHECK();
     return SA_OK;
+}
+
+int sa_zerofier(void *out, const void *domain, size_t k, void *stream) {
+    if (k > (size_t)ZF_MAXK) return SA_ESIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = sizeof(fe) * (2 * k + 1);
+    static bool attr_done = false;
+    if (!attr_done) {
+        SA_CUDA(cudaFuncSetAttribute(k_zerofier, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(fe) * (2 * ZF_MAXK + 1))));
+        attr_done = true;
+    }
+    k_zerofier<<<1, ZF_THREADS, smem, st>>>((fe *)out, (const fe *)domain, (int)k);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+int sa_interpolate(void *out, const void *domain, const void *values, size_t k, void *stream) {
+    if (k == 0) return SA_OK;
+    if (k > 2 * (size_t)ZF_MAXK) return SA_ESIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // workspace: z (k+1) | w (k) | flag | QT (k*k)
+    char *ws = nullptr;
+    const size_t z_off = 0, w_off = sizeof(fe) * (k + 1), f_off = w_off + sizeof(fe) * k,
+                 q_off = f_off + 16, total = q_off + sizeof(fe) * k * k;
+    int rc = get_workspace((void **)&ws, total, st, 7);
+    if (rc != SA_OK) return rc;
+    fe *z = (fe *)(ws + z_off), *w = (fe *)(ws + w_off), *QT = (fe *)(ws + q_off);
+    int *flag = (int *)(ws + f_off);
+    if (k <= (size_t)ZF_MAXK) {
+        if ((rc = sa_zerofier(z, domain, k, stream)) != SA_OK) return rc;
+    } else {  // two halves multiplied on the host side is the caller's job (ntt.py recursion)
+        return SA_ESIZE;
+    }
+    SA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const int bs = 128, grid = (int)((k + bs - 1) / bs);
+    k_interp_weights<<<grid, bs, 0, st>>>(w, (const fe *)domain, (const fe *)values, z, (int)k, flag);
+    SA_LAUNCH_CHECK();
+    k_interp_rows<<<grid, bs, 0, st>>>(QT, (const fe *)domain, w, z, (int)k);
+    SA_LAUNCH_CHECK();
+    k_interp_colsum<<<(unsigned)k, 256, 0, st>>>((fe *)out, QT, (int)k);
+    SA_LAUNCH_CHECK();
+    int h = 0;
+    SA_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    return h ? SA_EDIVZERO : SA_OK;
 }
 
 // ---- Merkle / FRI ----

@@ -22,8 +22,6 @@ import sa_marshal
 
 _P = sa_engine.P
 
-# below this many points the subproduct-tree helpers stop recursing and use one
-# device kernel per node (see fast_zerofier / fast_evaluate)
 _ORDER_MSG = "supplied root does not have supplied order"
 _PRIM_MSG = "supplied root is not primitive root of supplied order"
 
@@ -128,8 +126,15 @@ def fast_zerofier(domain, primitive_root, root_order):
     _check_root(primitive_root, root_order)
     if len(domain) == 0:
         return Polynomial([])
+    field = primitive_root.field
     if len(domain) == 1:
-        return Polynomial([-domain[0], primitive_root.field.one()])
+        return Polynomial([-domain[0], field.one()])
+    eng = _engine()
+    if len(domain) <= eng.MAX_DIRECT_POINTS:
+        # prod (X - d): the subproduct tree of ntt.py:76-80 yields this same monic polynomial,
+        # len(domain) + 1 coefficients; one device kernel builds it
+        _check_field(field)
+        return Polynomial(_unpack(eng.zerofier(eng.upload(sa_marshal.pack(domain))), field))
     half = len(domain) // 2
     left = fast_zerofier(domain[:half], primitive_root, root_order)
     right = fast_zerofier(domain[half:], primitive_root, root_order)
@@ -159,6 +164,15 @@ def fast_interpolate(domain, values, primitive_root, root_order):
         return Polynomial([])
     if len(domain) == 1:
         return Polynomial([values[0]])
+    eng = _engine()
+    if len(domain) <= eng.MAX_DIRECT_POINTS:
+        # the interpolant of degree < len(domain) is unique, so the device Lagrange kernels
+        # return exactly the len(domain) coefficients the recursion of ntt.py:113-130 produces;
+        # coinciding domain points raise "divide by zero" like the division at ntt.py:124-125
+        field = values[0].field
+        _check_field(field)
+        coeffs = eng.interpolate(eng.upload(sa_marshal.pack(domain)), eng.upload(sa_marshal.pack(values)))
+        return Polynomial(_unpack(coeffs, field))
     half = len(domain) // 2
     left_zerofier = fast_zerofier(domain[:half], primitive_root, root_order)
     right_zerofier = fast_zerofier(domain[half:], primitive_root, root_order)
@@ -215,4 +229,4 @@ def fast_coset_divide(lhs, rhs, offset, primitive_root, root_order):  # clean di
     quotient_codeword = eng.pointwise_div(a, b)  # raises "divide by zero" like algebra.py:92
     scaled_quotient = eng.ntt(quotient_codeword, _log2(eng.length(quotient_codeword)), root, inverse=True)
     kept = eng.slice(scaled_quotient, 0, lhs_degree - rhs_degree + 1)
-    return Polynomial(_unpack(eng.scale(kept, pow(offset.value, -1, field.p)), field))
+    return Polynomial(_unpack(eng.scale(kept, offset.inverse().value), field))

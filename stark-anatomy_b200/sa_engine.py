@@ -40,6 +40,8 @@ SYMBOLS = [
     ("sa_pointwise_div", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_scale", _ci, [_vp, _vp, _sz, _u64p, _vp]),
     ("sa_poly_eval", _ci, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    ("sa_zerofier", _ci, [_vp, _vp, _sz, _vp]),
+    ("sa_interpolate", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_merkle_tree", _ci, [_vp, _vp, _sz, _vp]),
     ("sa_merkle_open", _ci, [_vp, _vp, _sz, _u64p, _sz, _vp]),
     ("sa_gather", _ci, [_vp, _vp, _sz, _u64p, _sz, _vp]),
@@ -168,6 +170,21 @@ class CudaEngine:
         out = self.empty(points.shape[0])
         self._check(self.lib.sa_poly_eval(out.data_ptr(), coeffs.data_ptr(), coeffs.shape[0], points.data_ptr(),
                                           points.shape[0], self._stream()))
+        return out
+
+    MAX_DIRECT_POINTS = 4096  # sa_zerofier / sa_interpolate handle this many points per call
+
+    def zerofier(self, domain):
+        domain = domain.contiguous()
+        out = self.empty(domain.shape[0] + 1)
+        self._check(self.lib.sa_zerofier(out.data_ptr(), domain.data_ptr(), domain.shape[0], self._stream()))
+        return out
+
+    def interpolate(self, domain, values):
+        domain, values = domain.contiguous(), values.contiguous()
+        out = self.empty(domain.shape[0])
+        self._check(self.lib.sa_interpolate(out.data_ptr(), domain.data_ptr(), values.data_ptr(), domain.shape[0],
+                                            self._stream()))
         return out
 
     # --------------------------------------------------------------- merkle

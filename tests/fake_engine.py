@@ -80,6 +80,19 @@ class OracleEngine:
         self._log("poly_eval", coeffs.shape[0], points.shape[0])
         return O.poly_eval_np(coeffs, points)
 
+    MAX_DIRECT_POINTS = 4096
+
+    def zerofier(self, domain):
+        self._log("zerofier", domain.shape[0])
+        return O.zerofier_np(domain)
+
+    def interpolate(self, domain, values):
+        self._log("interpolate", domain.shape[0])
+        try:
+            return O.interpolate_np(domain, values)
+        except AssertionError:
+            raise SaError(SA_ERRORS[-4])
+
     def merkle_tree(self, vec):
         self._log("merkle_tree", vec.shape[0])
         return O.merkle_tree_np(vec)

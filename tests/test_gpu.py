@@ -148,6 +148,25 @@ def test_elementwise_ops(eng):
     assert (down(eng, eng.poly_eval(up(eng, coeffs), up(eng, pts))) == O.poly_eval_np(coeffs, pts)).all()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 17, 284, 1000, 4096])
+def test_zerofier_and_interpolate(eng, k):
+    dom = rand_np(70 + k, k)
+    vals = rand_np(71 + k, k)
+    z = down(eng, eng.zerofier(up(eng, dom)))
+    assert (z == O.zerofier_np(dom)).all()
+    if k <= 1000:
+        got = down(eng, eng.interpolate(up(eng, dom), up(eng, vals)))
+        assert (got == O.interpolate_np(dom, vals)).all()
+    else:  # full size: property check, the interpolant takes the prescribed values
+        poly = eng.interpolate(up(eng, dom), up(eng, vals))
+        assert (down(eng, eng.poly_eval(poly, up(eng, dom))) == vals).all()
+        assert (down(eng, eng.poly_eval(up(eng, z), up(eng, dom))) == 0).all()
+    if k >= 3:
+        dom[k - 1] = dom[0]
+        with pytest.raises(AssertionError, match="divide by zero"):
+            eng.interpolate(up(eng, dom), up(eng, vals))
+
+
 @pytest.mark.parametrize("log_n", [0, 1, 2, 5, 9, 10, 11, 14, 17])
 def test_merkle_tree_and_open(eng, log_n):
     n = 1 << log_n

@@ -120,13 +120,13 @@ def test_poly_golden():
     for c in g["zerofier"]:
         dom, zf = ints(c["domain"]), ints(c["out"])
         if dom:
-            assert len(zf) == len(dom) + 1 and zf[-1] == 1
-            assert O.from_np(O.poly_eval_np(O.to_np(zf), O.to_np(dom))) == [0] * len(dom)
+            assert O.from_np(O.zerofier_np(O.to_np(dom))) == zf
     for c in g["interpolate"]:
         dom, vals, poly = ints(c["domain"]), ints(c["values"]), ints(c["out"])
         if dom:
-            assert len(poly) == len(dom)
-            assert O.from_np(O.poly_eval_np(O.to_np(poly), O.to_np(dom))) == vals
+            assert O.from_np(O.interpolate_np(O.to_np(dom), O.to_np(vals))) == poly
+    with pytest.raises(AssertionError, match="divide by zero"):
+        O.interpolate_np(O.to_np([5, 7, 5]), O.to_np([1, 2, 3]))
 
 
 @pytest.mark.slow
