@@ -8,7 +8,7 @@
 namespace sa {
 
 constexpr int MK_THREADS = 256;  // threads per Merkle CTA
-constexpr int MK_CHUNK = 512;    // bottom nodes reduced by one CTA (32 KB of digests in smem)
+constexpr int MK_MAX_IPT_LOG = 3;  // a thread reduces at most 8 bottom nodes privately
 
 // c'[i] = 2^-1 (a + b) + (alpha * 2^-1 * x_i^-1) (a - b)   ==  fri.py:85
 //   inv2_m : 2^-1 in Montgomery form
@@ -22,7 +22,8 @@ SA_HD fe fri_fold_one(const fe &a, const fe &b, const fe &t_m, const fe &inv2_m)
 struct MerkleArgs {
     uint64_t *tree;      // heap layout, 8 words per node
     long long width;     // number of bottom nodes of this launch
-    int chunk;           // bottom nodes per CTA = min(MK_CHUNK, width)
+    int chunk;           // bottom nodes per CTA (power of two, <= MK_THREADS << ipt_log)
+    int ipt_log;         // log2 of the bottom nodes one thread reduces privately (0..3)
     int mode;            // 0: bottom digests already in tree; 1: leaves from `values`; 2: leaves from a fold
     const fe *values;    // mode 1: the codeword (width elements)
     const fe *prev;      // mode 2: the codeword being folded (2 * width elements)
@@ -32,9 +33,28 @@ struct MerkleArgs {
     fe inv2_m;           // mode 2: 2^-1 in Montgomery form
 };
 
-// bottom digest j (0 <= j < chunk) of CTA `blk`; writes tree (and next[] in mode 2)
-SA_HD void merkle_bottom(uint64_t d[8], const MerkleArgs &a, long long blk, int j) {
-    const long long g = blk * a.chunk + j;  // global bottom index
+// launch shape for a level of `width` bottom nodes: small levels are latency bound (one node per
+// thread, as many CTAs as possible), big ones throughput bound (four leaves and their three
+// parents per thread, no barrier in between)
+SA_HD void merkle_shape(MerkleArgs &a) {
+    if (a.width <= MK_THREADS) {  // one CTA finishes the tree
+        a.ipt_log = 0;
+        a.chunk = (int)a.width;
+    } else if (a.width < (1 << 17)) {  // <= one wave of 256-node CTAs: shortest dependency chain
+        a.ipt_log = 0;
+        a.chunk = MK_THREADS;
+    } else if (a.width < (1 << 18)) {
+        a.ipt_log = 1;
+        a.chunk = MK_THREADS << 1;
+    } else {  // throughput bound: 4 bottom nodes + their 3 parents per thread, barrier free
+        a.ipt_log = 2;
+        a.chunk = MK_THREADS << 2;
+    }
+}
+
+// digest of bottom node g of this launch: loads it (mode 0) or hashes the leaf (modes 1, 2) and
+// writes it to the tree (and next[] in mode 2)
+SA_HD void merkle_bottom(uint64_t d[8], const MerkleArgs &a, long long g) {
     uint64_t *node = a.tree + (a.width + g) * 8;
     if (a.mode == 0) {
         for (int i = 0; i < 8; i++) d[i] = node[i];
@@ -50,6 +70,31 @@ SA_HD void merkle_bottom(uint64_t d[8], const MerkleArgs &a, long long blk, int 
     }
     merkle_leaf_digest(d, v);
     for (int i = 0; i < 8; i++) node[i] = d[i];
+}
+
+// Private phase of thread t of CTA blk: reduce its 2^ipt_log bottom nodes to one digest (streaming:
+// a slot per height), writing every node it creates to the tree.  root = the subtree digest.
+SA_HD void merkle_private(uint64_t root[8], const MerkleArgs &a, long long blk, int t) {
+    uint64_t slot[MK_MAX_IPT_LOG][8];
+    const int ipt = 1 << a.ipt_log;
+    uint64_t d[8];
+    for (int j = 0; j < ipt; j++) {
+        const long long g = blk * a.chunk + (long long)t * ipt + j;
+        merkle_bottom(d, a, g);
+        long long idx = a.width + g;
+        int h = 0;
+        while ((j >> h) & 1) {  // a left sibling of this height is waiting: combine
+            uint64_t l[8];
+            for (int i = 0; i < 8; i++) l[i] = slot[h][i];
+            merkle_node_digest(d, l, d);
+            idx >>= 1;
+            for (int i = 0; i < 8; i++) a.tree[idx * 8 + i] = d[i];
+            h++;
+        }
+        if (h < a.ipt_log)
+            for (int i = 0; i < 8; i++) slot[h][i] = d[i];
+    }
+    for (int i = 0; i < 8; i++) root[i] = d[i];
 }
 
 }  // namespace sa

@@ -58,7 +58,12 @@ SA_HD uint64_t b2_rotr(uint64_t x, int r) {
 
 // digest (8 words) of a message that fits one 128-byte block; len = message bytes,
 // m[] zero padded.  h0 = IV ^ parameter block (0x01010040 into word 0).
-SA_HD void blake2b_single_block(uint64_t out[8], const uint64_t m[16], uint32_t len) {
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void blake2b_single_block(uint64_t out[8], const uint64_t m[16], uint32_t len) {
     const uint64_t iv0 = 0x6a09e667f3bcc908ULL, iv1 = 0xbb67ae8584caa73bULL, iv2 = 0x3c6ef372fe94f82bULL,
                    iv3 = 0xa54ff53a5f1d36f1ULL, iv4 = 0x510e527fade682d1ULL, iv5 = 0x9b05688c2b3e6c1fULL,
                    iv6 = 0x1f83d9abfb41bd6bULL, iv7 = 0x5be0cd19137e2179ULL;
@@ -185,6 +190,7 @@ SA_HD void merkle_leaf_digest(uint64_t out[8], const fe &x) {
 }
 
 // node digest of two child digests
+// (out may alias left or right)
 SA_HD void merkle_node_digest(uint64_t out[8], const uint64_t left[8], const uint64_t right[8]) {
     uint64_t m[16];
 #if defined(__CUDA_ARCH__)

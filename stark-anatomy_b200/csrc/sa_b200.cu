@@ -252,25 +252,30 @@ __global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xin
 }
 
 // One CTA reduces `chunk` bottom nodes to one node, writing every level to the heap-ordered tree.
-// mode 2 is the fused FRI round: fold -> leaf digest -> subtree, one pass over the codeword.
+// Phase 1: every thread reduces its 2^ipt_log bottom nodes privately (no barrier); phase 2: the
+// per-thread digests are reduced through shared memory.  mode 2 is the fused FRI round:
+// fold -> leaf digest -> subtree, one pass over the codeword.
 __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
-    __shared__ uint64_t sm[MK_CHUNK * 8];
+    __shared__ uint64_t sm[MK_THREADS * 8];
     const int tid = threadIdx.x;
     const long long blk = blockIdx.x;
+    const int active = a.chunk >> a.ipt_log;  // threads with a private subtree
     uint64_t d[8];
-    for (int j = tid; j < a.chunk; j += MK_THREADS) {
-        merkle_bottom(d, a, blk, j);
+    if (tid < active) {
+        merkle_private(d, a, blk, tid);
 #pragma unroll
-        for (int i = 0; i < 8; i++) sm[j * 8 + i] = d[i];
+        for (int i = 0; i < 8; i++) sm[tid * 8 + i] = d[i];
     }
     __syncthreads();
-    long long gw = a.width / 2;  // global width of the level being produced
-    for (int wl = a.chunk / 2; wl >= 1; wl >>= 1, gw >>= 1) {
+    // index of thread 0's subtree root; the level above it starts at base >> 1, and so on
+    long long base = (a.width + blk * a.chunk) >> a.ipt_log;
+    for (int wl = active / 2; wl >= 1; wl >>= 1) {
+        base >>= 1;
         const bool mine = tid < wl;
         if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
         __syncthreads();
         if (mine) {
-            uint64_t *node = a.tree + (gw + blk * wl + tid) * 8;
+            uint64_t *node = a.tree + (base + tid) * 8;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 sm[tid * 8 + i] = d[i];
@@ -742,11 +747,11 @@ int sa_interpolate(void *out, const void *domain, const void *values, size_t k, 
 static int merkle_reduce(MerkleArgs a, cudaStream_t st) {
     // first launch handles the bottom level in a.mode, later launches continue from digests
     while (true) {
-        a.chunk = (int)(a.width < MK_CHUNK ? a.width : MK_CHUNK);
+        merkle_shape(a);
         k_merkle_chunk<<<(unsigned)(a.width / a.chunk), MK_THREADS, 0, st>>>(a);
         SA_LAUNCH_CHECK();
-        if (a.width <= MK_CHUNK) break;
-        a.width /= MK_CHUNK;
+        if (a.width <= a.chunk) break;
+        a.width /= a.chunk;
         a.mode = 0;
     }
     return SA_OK;

@@ -33,11 +33,66 @@ from hashlib import blake2b
 from univariate import *  # noqa: F401,F403
 from univariate import Polynomial, test_colinearity
 from algebra import FieldElement
-from merkle import Merkle
+from merkle import Merkle as _HostMerkle
 from ntt import intt
 
 import sa_engine
 import sa_marshal
+
+
+class Merkle(_HostMerkle):
+    """code/merkle.py's Merkle with ``commit`` / ``open`` on the GPU for field-element data.
+
+    code/fast_stark.py calls ``Merkle.commit(codeword)`` once and then ``Merkle.open(i, codeword)``
+    hundreds of times on the same list (fast_stark.py:105,118,162-174); the reference re-hashes
+    every leaf per call (merkle.py:26-27).  Here the packed list is fingerprinted (blake2b of the
+    16-byte limbs, on the host) and its device tree is kept in a small cache, so an ``open`` is one
+    path gather.  Leaves are blake2b(decimal ASCII of the value) exactly as merkle.py:14 +
+    algebra.py:53-57.  Data that is not a list of field elements of p = 1 + 407*2^119 (e.g. the raw
+    byte strings of code/test_merkle.py) is outside the engine's domain and goes through the
+    caller's own host class unchanged.  ``verify`` / ``verify_`` / ``commit_`` / ``open_`` are the
+    host class's (verifier side, digests in and out).
+    """
+
+    _trees = {}           # fingerprint -> device tree, insertion ordered
+    _cache_bytes = 0
+    _CACHE_LIMIT = 1 << 30
+
+    def _device_tree(data_array):
+        n = len(data_array)
+        if n == 0 or n & (n - 1):
+            return None
+        first = data_array[0]
+        if not isinstance(first, FieldElement) or first.field.p != sa_engine.P:
+            return None
+        try:
+            packed = sa_marshal.pack(data_array)
+        except (TypeError, AttributeError, OverflowError):
+            return None
+        key = blake2b(packed, digest_size=32).digest()
+        tree = Merkle._trees.get(key)
+        if tree is None:
+            eng = sa_engine.get_engine()
+            tree = eng.merkle_tree(eng.upload(packed))
+            Merkle._trees[key] = tree
+            Merkle._cache_bytes += 128 * n
+            while Merkle._cache_bytes > Merkle._CACHE_LIMIT and len(Merkle._trees) > 1:
+                old = next(iter(Merkle._trees))
+                Merkle._cache_bytes -= 64 * Merkle._trees.pop(old).shape[0]
+        return tree
+
+    def commit(data_array):
+        tree = Merkle._device_tree(data_array)
+        if tree is None:
+            return _HostMerkle.commit(data_array)
+        return sa_engine.get_engine().tree_root(tree)
+
+    def open(index, data_array):
+        tree = Merkle._device_tree(data_array)
+        if tree is None or len(data_array) < 2:
+            return _HostMerkle.open(index, data_array)
+        assert(0 <= index and index < len(data_array)), "cannot open invalid index"
+        return sa_engine.get_engine().merkle_open(tree, [index])[0]
 
 
 class DeviceCodeword:

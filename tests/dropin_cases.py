@@ -232,3 +232,34 @@ def case_faststark_trace_replay():
         assert idx == rec["indices"]
         want = [T.dec_obj(o) for o in rec["pushed"]]
         assert [pickle.dumps(o) for o in ps.objects[before:]] == [pickle.dumps(o) for o in want]
+
+
+# --------------------------------------------------------------------- merkle
+def case_merkle_class():
+    """fri.Merkle (GPU commit/open for field elements) against the reference's outputs"""
+    g = load_golden("merkle.json")
+    by_key = {}
+    for c in g["commit"]:
+        if "in" in c:
+            xs = T.elems(c["in"])
+        elif c["n"] <= 1 << 14:
+            xs = seeded(c["seed"], c["n"])
+        else:
+            continue
+        by_key[(str(c["seed"]), c["n"])] = xs
+        assert F.Merkle.commit(xs).hex() == c["root"]
+    for c in g["open"]:
+        xs = by_key[(str(c["seed"]), c["n"])]
+        path = F.Merkle.open(c["index"], xs)
+        assert [p.hex() for p in path] == c["path"]
+        assert F.Merkle.verify(F.Merkle.commit(xs), c["index"], path, xs[c["index"]])
+        assert not F.Merkle.verify(F.Merkle.commit(xs), c["index"] ^ 1, path, xs[c["index"]])
+    xs = seeded(9, 64)
+    with pytest.raises(AssertionError, match="cannot open invalid index"):
+        F.Merkle.open(64, xs)
+    # raw byte strings (code/test_merkle.py's data) stay on the caller's host class
+    import os
+    data = [os.urandom(int(os.urandom(1)[0]) + 1) for _ in range(16)]
+    root = F.Merkle.commit(data)
+    for i in range(16):
+        assert F.Merkle.verify(root, i, F.Merkle.open(i, data), data[i])

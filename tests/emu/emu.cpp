@@ -167,21 +167,19 @@ void emu_node_digest(uint8_t *out64, const uint8_t *left, const uint8_t *right) 
     memcpy(out64, d, 64);
 }
 
-// mirrors merkle_reduce / k_merkle_chunk (sa_b200.cu): chunked reduction, heap-ordered tree
+// mirrors merkle_reduce / k_merkle_chunk (sa_b200.cu): private subtrees, then the shared-memory
+// reduction, heap-ordered tree
 static void emu_merkle_reduce(MerkleArgs a) {
-    std::vector<uint64_t> sm((size_t)MK_CHUNK * 8);
+    std::vector<uint64_t> sm((size_t)MK_THREADS * 8);
     while (true) {
-        a.chunk = (int)(a.width < MK_CHUNK ? a.width : MK_CHUNK);
+        merkle_shape(a);
         const long long blocks = a.width / a.chunk;
+        const int active = a.chunk >> a.ipt_log;
         for (long long blk = 0; blk < blocks; blk++) {
-            uint64_t d[8];
-            for (int tid = 0; tid < MK_THREADS; tid++)
-                for (int j = tid; j < a.chunk; j += MK_THREADS) {
-                    merkle_bottom(d, a, blk, j);
-                    for (int i = 0; i < 8; i++) sm[(size_t)j * 8 + i] = d[i];
-                }
-            long long gw = a.width / 2;
-            for (int wl = a.chunk / 2; wl >= 1; wl >>= 1, gw >>= 1) {
+            for (int tid = 0; tid < active; tid++) merkle_private(&sm[(size_t)tid * 8], a, blk, tid);
+            long long base = (a.width + blk * a.chunk) >> a.ipt_log;
+            for (int wl = active / 2; wl >= 1; wl >>= 1) {
+                base >>= 1;
                 std::vector<uint64_t> regs((size_t)wl * 8);
                 for (int tid = 0; tid < wl; tid++)  // phase 1: read children, hash
                     merkle_node_digest(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8],
@@ -189,12 +187,12 @@ static void emu_merkle_reduce(MerkleArgs a) {
                 for (int tid = 0; tid < wl; tid++)  // phase 2: publish
                     for (int i = 0; i < 8; i++) {
                         sm[(size_t)tid * 8 + i] = regs[(size_t)tid * 8 + i];
-                        a.tree[(gw + blk * wl + tid) * 8 + i] = regs[(size_t)tid * 8 + i];
+                        a.tree[(base + tid) * 8 + i] = regs[(size_t)tid * 8 + i];
                     }
             }
         }
-        if (a.width <= MK_CHUNK) break;
-        a.width /= MK_CHUNK;
+        if (a.width <= a.chunk) break;
+        a.width /= a.chunk;
         a.mode = 0;
     }
 }

@@ -60,6 +60,10 @@ def test_faststark_trace_replay():
     C.case_faststark_trace_replay()
 
 
+def test_merkle_class():
+    C.case_merkle_class()
+
+
 def test_engine_use_is_recorded():
     """the drop-in really goes through the engine object (no hidden host arithmetic)"""
     eng = sa_engine.get_engine()

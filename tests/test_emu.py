@@ -98,7 +98,7 @@ def test_decimal_and_leaf(E):
         assert d.tobytes() == hashlib.blake2b(l + r).digest()
 
 
-@pytest.mark.parametrize("logn", [0, 1, 2, 5, 9, 10, 11, 12])
+@pytest.mark.parametrize("logn", [0, 1, 2, 5, 8, 9, 10, 11, 12, 15, 16])
 def test_merkle_and_fri_round(E, logn):
     rng = random.Random(40 + logn)
     n = 1 << logn

@@ -242,5 +242,9 @@ def test_dropin_faststark_trace_replay(eng):
     C.case_faststark_trace_replay()
 
 
+def test_dropin_merkle_class(eng):
+    C.case_merkle_class()
+
+
 def test_kernels_were_launched(eng):
     assert eng.launch_count() > 100
