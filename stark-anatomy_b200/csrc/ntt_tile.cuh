@@ -45,6 +45,10 @@ struct TileArgs {
     fe cst[8];  // cst[k] = w_16^k (Montgomery form) when L >= 16, else w_L^k; k < 8
 };
 
+// kernel variants: with TF_DYNAMIC everything is decided at run time (partial tiles, optional
+// output twiddle / scale); the static variants drop the predication and branches
+enum { TF_FULL = 1, TF_TWB = 2, TF_SCALE = 4, TF_DYNAMIC = 8 };
+
 template <int LOGL, int ELOG, int C>
 struct TilePlan {
     static constexpr int L = 1 << LOGL;
@@ -151,7 +155,7 @@ SA_HD void tile_st(fe *p, const fe &x) {
 
 // A full-radix (E-point) stage that is NOT the last stage: one unit per thread.
 //   ml = log2 M of this stage (run-time, so all such stages share one copy of the code)
-template <int LOGL, int ELOG, int C>
+template <int LOGL, int ELOG, int C, int FLAGS>
 SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid, bool first,
                                int ml) {
     using P = TilePlan<LOGL, ELOG, C>;
@@ -159,17 +163,19 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
     constexpr int CSTEP = 16 / R;  // a non-last stage exists only when L > E >= 8, so cst = w_16^k
     const int c = t % C, q = t / C;
     const int col = col0 + c;
-    const bool active = valid && col < a.ncols;
+    const bool active = (FLAGS & TF_FULL) ? true : (valid && col < a.ncols);
     const int M = 1 << ml, wlog = LOGL - ml - P::EL;
     const int K = q >> ml, m = q & (M - 1);
     const int row0 = (K << (ml + P::EL)) + m;
     fe x[R];
     if (first) {
         const fe *src = a.in + b * a.in_sb + (long long)col * a.in_sc;
+        // row offsets fit 32 bits (row < 1024, stride <= 2^20): one IMAD.WIDE per address
+        const unsigned sr = (unsigned)a.in_sr, step = (unsigned)M * sr, off0 = (unsigned)row0 * sr;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (long long)(row0 + d * M) * a.in_sr) : fe_zero();
+        for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (off0 + (unsigned)d * step)) : fe_zero();
     } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -189,7 +195,7 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
 }
 
 // The last stage (radix 2^LASTLOG, M = 1): E / R units per thread, output twiddle, global stores.
-template <int LOGL, int ELOG, int C>
+template <int LOGL, int ELOG, int C, int FLAGS>
 SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
     using P = TilePlan<LOGL, ELOG, C>;
     constexpr int R = 1 << P::LASTLOG, U = P::E / R;
@@ -197,7 +203,11 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
     constexpr int CSTEP = LOGL >= 4 ? 16 / R : (1 << LOGL) / R;
     const int c = t % C, q = t / C;
     const int col = col0 + c;
-    const bool active = valid && col < a.ncols;
+    const bool active = (FLAGS & TF_FULL) ? true : (valid && col < a.ncols);
+    const bool use_twb = (FLAGS & TF_DYNAMIC) ? (a.twb != nullptr) : ((FLAGS & TF_TWB) != 0);
+    const bool use_scale = (FLAGS & TF_DYNAMIC) ? (a.has_scale != 0) : ((FLAGS & TF_SCALE) != 0);
+    const fe *twb = use_twb ? a.twb + col : nullptr;
+    const unsigned out_sr = (unsigned)a.out_sr, twb_sr = (unsigned)a.twb_stride;
     fe *dst = a.out + b * a.out_sb + (long long)col * a.out_sc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -210,7 +220,7 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (long long)(row0 + d) * a.in_sr) : fe_zero();
+            for (int d = 0; d < R; d++) x[d] = active ? tile_ld(src + (unsigned)(row0 + d) * (unsigned)a.in_sr) : fe_zero();
         } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -222,27 +232,36 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
 #pragma unroll
 #endif
         for (int k = 0; k < R; k++) {
-            const int o = tile_digit_reverse<LOGL, ELOG, C>(row0 + k);
+            const unsigned o = (unsigned)tile_digit_reverse<LOGL, ELOG, C>(row0 + k);
             fe v = x[k];
-            if (a.twb != nullptr && active) v = fe_montmul(v, tile_ldg(a.twb + (long long)o * a.twb_stride + col));
-            if (a.has_scale) v = fe_montmul(v, a.scale);
-            if (active) tile_st(dst + (long long)o * a.out_sr, v);
+            if (use_twb && active) v = fe_montmul(v, tile_ldg(twb + o * twb_sr));
+            if (use_scale) v = fe_montmul(v, a.scale);
+            if (active) tile_st(dst + o * out_sr, v);
         }
     }
 }
 
 // the whole tile for thread t; `sync` is __syncthreads on the device and a no-op marker on
 // the host (the emulator calls the stages phase by phase instead)
-template <int LOGL, int ELOG, int C>
+template <int LOGL, int ELOG, int C, int FLAGS = TF_DYNAMIC>
 struct TileStages {
     using P = TilePlan<LOGL, ELOG, C>;
     // stage index st < NLOOP -> full stage with ml = LOGL - (st + 1) * EL
     SA_HD static void full(int st, int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
-        ntt_tile_full_stage<LOGL, ELOG, C>(t, sm, a, b, col0, valid, st == 0, LOGL - (st + 1) * P::EL);
+        ntt_tile_full_stage<LOGL, ELOG, C, FLAGS>(t, sm, a, b, col0, valid, st == 0, LOGL - (st + 1) * P::EL);
     }
     SA_HD static void last(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
-        ntt_tile_last_stage<LOGL, ELOG, C>(t, sm, a, b, col0, valid);
+        ntt_tile_last_stage<LOGL, ELOG, C, FLAGS>(t, sm, a, b, col0, valid);
     }
 };
+
+// which static variant (if any) fits these arguments; TF_DYNAMIC otherwise
+template <int LOGL, int ELOG, int C>
+SA_HD int tile_variant(const TileArgs &a) {
+    using P = TilePlan<LOGL, ELOG, C>;
+    const long long tiles = (long long)((a.ncols + C - 1) / C) * a.nbatch;
+    if (LOGL < 5 || a.ncols % C != 0 || tiles % P::TPC != 0 || a.has_scale) return TF_DYNAMIC;
+    return TF_FULL | (a.twb != nullptr ? TF_TWB : 0);
+}
 
 }  // namespace sa

@@ -67,11 +67,11 @@ struct TileLaunch {
     static constexpr int MINB = TARGET / P::THREADS > 0 ? TARGET / P::THREADS : 1;
 };
 
-template <int LOGL, int ELOG, int C>
+template <int LOGL, int ELOG, int C, int FLAGS>
 __global__ void __launch_bounds__(TilePlan<LOGL, ELOG, C>::THREADS, TileLaunch<LOGL, ELOG, C>::MINB)
     ntt_tile_kernel(const __grid_constant__ TileArgs a, long long total_tiles, int tiles_per_batch) {
     using P = TilePlan<LOGL, ELOG, C>;
-    using S = TileStages<LOGL, ELOG, C>;
+    using S = TileStages<LOGL, ELOG, C, FLAGS>;
     extern __shared__ uint4 sa_smem_u4[];
     fe *smem = reinterpret_cast<fe *>(sa_smem_u4);
     const int tic = threadIdx.x / P::TPT, t = threadIdx.x % P::TPT;
@@ -476,8 +476,8 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
     return SA_OK;
 }
 
-template <int LOGL, int ELOG, int C>
-static int launch_tile(const TileArgs &a, cudaStream_t st) {
+template <int LOGL, int ELOG, int C, int FLAGS>
+static int launch_tile_variant(const TileArgs &a, cudaStream_t st) {
     using P = TilePlan<LOGL, ELOG, C>;
     const int tiles_per_batch = (a.ncols + C - 1) / C;
     const long long total = (long long)tiles_per_batch * a.nbatch;
@@ -485,13 +485,23 @@ static int launch_tile(const TileArgs &a, cudaStream_t st) {
     const size_t smem = P::smem_bytes();
     static bool attr_done = false;
     if (smem > 48 * 1024 && !attr_done) {
-        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL, ELOG, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL, ELOG, C, FLAGS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    ntt_tile_kernel<LOGL, ELOG, C><<<(unsigned)grid, P::THREADS, smem, st>>>(a, total, tiles_per_batch);
+    ntt_tile_kernel<LOGL, ELOG, C, FLAGS><<<(unsigned)grid, P::THREADS, smem, st>>>(a, total, tiles_per_batch);
     SA_LAUNCH_CHECK();
     return SA_OK;
+}
+template <int LOGL, int ELOG, int C>
+static int launch_tile(const TileArgs &a, cudaStream_t st) {
+    if constexpr (LOGL >= 5) {
+        switch (tile_variant<LOGL, ELOG, C>(a)) {
+            case TF_FULL | TF_TWB: return launch_tile_variant<LOGL, ELOG, C, TF_FULL | TF_TWB>(a, st);
+            case TF_FULL: return launch_tile_variant<LOGL, ELOG, C, TF_FULL>(a, st);
+        }
+    }
+    return launch_tile_variant<LOGL, ELOG, C, TF_DYNAMIC>(a, st);
 }
 
 // tile shape: register block (log2 elements per thread) and columns per tile; with -DSA_TUNE

@@ -24,10 +24,10 @@ static fe from_limbs(const uint64_t x[2]) {
 
 static int g_elog = 4, g_c = 8;  // tile shape under test (emu_set_shape)
 
-template <int LOGL, int ELOG, int C>
-static void run_tiles(const TileArgs &a) {
+template <int LOGL, int ELOG, int C, int FLAGS>
+static void run_tiles_variant(const TileArgs &a) {
     using P = TilePlan<LOGL, ELOG, C>;
-    using S = TileStages<LOGL, ELOG, C>;
+    using S = TileStages<LOGL, ELOG, C, FLAGS>;
     const int tiles_per_batch = (a.ncols + C - 1) / C;
     const long long total = (long long)tiles_per_batch * a.nbatch;
     std::vector<fe> sm((size_t)P::L * C);
@@ -39,6 +39,16 @@ static void run_tiles(const TileArgs &a) {
             for (int t = 0; t < P::TPT; t++) S::full(st, t, sm.data(), a, b, col0, true);
         for (int t = 0; t < P::TPT; t++) S::last(t, sm.data(), a, b, col0, true);
     }
+}
+template <int LOGL, int ELOG, int C>
+static void run_tiles(const TileArgs &a) {  // same variant choice as launch_tile (sa_b200.cu)
+    if constexpr (LOGL >= 5) {
+        switch (tile_variant<LOGL, ELOG, C>(a)) {
+            case TF_FULL | TF_TWB: return run_tiles_variant<LOGL, ELOG, C, TF_FULL | TF_TWB>(a);
+            case TF_FULL: return run_tiles_variant<LOGL, ELOG, C, TF_FULL>(a);
+        }
+    }
+    return run_tiles_variant<LOGL, ELOG, C, TF_DYNAMIC>(a);
 }
 template <int LOGL>
 static void run_tiles_shape(const TileArgs &a) {
