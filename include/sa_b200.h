@@ -39,7 +39,7 @@ enum {
     SA_ENOTPRIM = -3,   /* ntt.py:11  "primitive root is not primitive nth root of unity, ..." */
     SA_EDIVZERO = -4,   /* algebra.py:92 "divide by zero" (element-wise division, ntt.py:172) */
     SA_EINDEX = -5,     /* merkle.py:18 "cannot open invalid index" */
-    SA_ESIZE = -6,      /* unsupported size (log_n > 20, n == 0, ...) */
+    SA_ESIZE = -6,      /* unsupported size (log_n > 26, n == 0, ...) */
     SA_ECALLBACK = -7,  /* the challenge callback of sa_fri_commit returned non-zero */
     SA_ECUDA = -100     /* CUDA runtime error; sa_last_error() has the text */
 };

@@ -38,6 +38,9 @@ struct TileArgs {
     long long in_sr, in_sc, in_sb;     // element strides of (row, column, batch) on input
     long long out_sr, out_sc, out_sb;  // ... and on output
     long long twb_stride;
+    // batch item bb splits as (bb / inner, bb % inner): offset = (bb / inner) * sb + (bb % inner) * sb2
+    long long in_sb2, out_sb2;
+    int inner;   // 1 = plain batch
     int ncols;   // valid columns per batch item
     int nbatch;  // batch items
     int has_scale;
@@ -153,6 +156,10 @@ SA_HD void tile_st(fe *p, const fe &x) {
 #endif
 }
 
+SA_HD long long tile_batch_offset(long long b, int inner, long long sb, long long sb2) {
+    return inner <= 1 ? b * sb : (b / inner) * sb + (b % inner) * sb2;
+}
+
 // A full-radix (E-point) stage that is NOT the last stage: one unit per thread.
 //   ml = log2 M of this stage (run-time, so all such stages share one copy of the code)
 template <int LOGL, int ELOG, int C, int FLAGS>
@@ -169,7 +176,7 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
     const int row0 = (K << (ml + P::EL)) + m;
     fe x[R];
     if (first) {
-        const fe *src = a.in + b * a.in_sb + (long long)col * a.in_sc;
+        const fe *src = a.in + tile_batch_offset(b, a.inner, a.in_sb, a.in_sb2) + (long long)col * a.in_sc;
         // row offsets fit 32 bits (row < 1024, stride <= 2^20): one IMAD.WIDE per address
         const unsigned sr = (unsigned)a.in_sr, step = (unsigned)M * sr, off0 = (unsigned)row0 * sr;
 #if defined(__CUDA_ARCH__)
@@ -208,7 +215,7 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
     const bool use_scale = (FLAGS & TF_DYNAMIC) ? (a.has_scale != 0) : ((FLAGS & TF_SCALE) != 0);
     const fe *twb = use_twb ? a.twb + col : nullptr;
     const unsigned out_sr = (unsigned)a.out_sr, twb_sr = (unsigned)a.twb_stride;
-    fe *dst = a.out + b * a.out_sb + (long long)col * a.out_sc;
+    fe *dst = a.out + tile_batch_offset(b, a.inner, a.out_sb, a.out_sb2) + (long long)col * a.out_sc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -216,7 +223,7 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
         const int row0 = (q * U + s) * R;
         fe x[R];
         if (FIRST) {
-            const fe *src = a.in + b * a.in_sb + (long long)col * a.in_sc;
+            const fe *src = a.in + tile_batch_offset(b, a.inner, a.in_sb, a.in_sb2) + (long long)col * a.in_sc;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif

@@ -406,9 +406,9 @@ static void keep_pool_memory() {
 
 // ---------------------------------------------------------------- NTT plans --
 struct NttPlan {
-    int log_n = 0, l1 = 0, l2 = 0;
-    fe *tw1 = nullptr, *tw2 = nullptr, *twb = nullptr;
-    fe cst1[8], cst2[8];
+    int log_n = 0, l1 = 0, l2 = 0, l3 = 0;
+    fe *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twb = nullptr, *twb2 = nullptr;
+    fe cst1[8], cst2[8], cst3[8];
     fe scale_m;     // n^-1 (Montgomery) for single-tile inverse transforms
     int has_scale = 0;
 };
@@ -451,7 +451,31 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
     const NttShape shape = ntt_shape(log_n);
     p.l1 = shape.l1;
     p.l2 = shape.l2;
-    if (log_n <= 10) {
+    p.l3 = shape.l3;
+    if (shape.l3 > 0) {
+        const int n1 = 1 << p.l1, n2 = 1 << p.l2, n3 = 1 << p.l3;
+        const long long m = (long long)n2 * n3;
+        const fe w1_m = fe_mont_pow_u64(w_m, (uint64_t)m);     // n1-point transforms over j1
+        const fe wsub_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-m sub-transforms
+        const fe w2_m = fe_mont_pow_u64(wsub_m, (uint64_t)n3);
+        const fe w3_m = fe_mont_pow_u64(wsub_m, (uint64_t)n2);
+        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw3, w3_m, fe_mont_one(), n3, st)) != SA_OK) return rc;
+        ntt_fill_cst(p.cst1, w1_m, n1);
+        ntt_fill_cst(p.cst2, w2_m, n2);
+        ntt_fill_cst(p.cst3, w3_m, n3);
+        SA_CUDA(cudaMalloc(&p.twb, sizeof(fe) * (size_t)n));
+        SA_CUDA(cudaMalloc(&p.twb2, sizeof(fe) * (size_t)m));
+        const int bs = 128;
+        long long threads = (long long)n1 * ((m + 15) / 16);
+        k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(p.twb, w_m, inverse ? ninv_m : fe_mont_one(),
+                                                                      n1, (int)m);
+        SA_LAUNCH_CHECK();
+        threads = (long long)n2 * ((n3 + 15) / 16);
+        k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(p.twb2, wsub_m, fe_mont_one(), n2, n3);
+        SA_LAUNCH_CHECK();
+    } else if (log_n <= 10) {
         if ((rc = build_pow_table(&p.tw1, w_m, fe_mont_one(), (long long)n, st)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w_m, (int)n);
         p.has_scale = inverse ? 1 : 0;
@@ -557,7 +581,7 @@ uint64_t sa_launch_count(void) { return g_launches.load(); }
 int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
            void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (log_n < 0 || log_n > 20) return SA_ESIZE;
+    if (log_n < 0 || log_n > NTT_MAX_LOG_N) return SA_ESIZE;
     if (batch == 0) return SA_OK;
     const size_t n = size_t(1) << log_n;
     if (log_n == 0) {  // ntt.py:5-6 / :23-24: a length-1 sequence is returned as is
@@ -580,8 +604,19 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     shape.log_n = log_n;
     shape.l1 = p->l1;
     shape.l2 = p->l2;
+    shape.l3 = p->l3;
     fe *tmp = nullptr;
     if ((rc = get_workspace((void **)&tmp, sizeof(fe) * n * batch, st)) != SA_OK) return rc;
+    if (shape.l3 > 0) {
+        if (batch * ((size_t)1 << (p->l1 > p->l2 ? p->l1 : p->l2)) > ((size_t)1 << 30)) return SA_ESIZE;
+        // `out` doubles as the first intermediate (tiles read before they write: in == out is fine)
+        ntt_fill_3pass_a(a, (const fe *)in, (fe *)out, shape, batch, p->tw1, p->twb, p->cst1);
+        if ((rc = launch_tile_dyn(p->l1, a, st)) != SA_OK) return rc;
+        ntt_fill_3pass_b(a, (const fe *)out, tmp, shape, batch, p->tw2, p->twb2, p->cst2);
+        if ((rc = launch_tile_dyn(p->l2, a, st)) != SA_OK) return rc;
+        ntt_fill_3pass_c(a, tmp, (fe *)out, shape, batch, p->tw3, p->cst3);
+        return launch_tile_dyn(p->l3, a, st);
+    }
     ntt_fill_pass1(a, (const fe *)in, tmp, shape, batch, p->tw1, p->twb, p->cst1);
     rc = launch_tile_dyn(p->l1, a, st);
     if (rc == SA_OK) {
@@ -609,7 +644,7 @@ static int copy_streams_ready() {
 int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,
                 size_t batch, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (log_n < 0 || log_n > 20) return SA_ESIZE;
+    if (log_n < 0 || log_n > NTT_MAX_LOG_N) return SA_ESIZE;
     const size_t one = size_t(16) << log_n;
     const size_t bytes = one * batch;
     if (bytes == 0) return SA_OK;

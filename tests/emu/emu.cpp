@@ -111,8 +111,23 @@ void emu_inv(uint64_t *out, const uint64_t *a) {
     memcpy(out, &r, 16);
 }
 
-// mirrors sa_ntt (sa_b200.cu): same plan, same tile passes
-int emu_ntt(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, int inverse, size_t batch) {
+static std::vector<fe> twb_table(const fe &w_m, const fe &scale_m, size_t rows, size_t cols) {
+    std::vector<fe> t(rows * cols);
+    for (size_t k = 0; k < rows; k++) {
+        const fe wk = fe_mont_pow_u64(w_m, k);
+        fe acc = scale_m;
+        for (size_t j = 0; j < cols; j++) {
+            t[k * cols + j] = acc;
+            acc = fe_montmul(acc, wk);
+        }
+    }
+    return t;
+}
+
+// mirrors sa_ntt (sa_b200.cu): same plan, same tile passes.  force3 != 0 uses the three-pass
+// split (normally only for log_n > 20) so that it can be exercised at small sizes.
+int emu_ntt_ex(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, int inverse, size_t batch,
+               int force3) {
     const size_t n = size_t(1) << log_n;
     if (log_n == 0) {
         memcpy(out, in, 16 * batch);
@@ -123,31 +138,44 @@ int emu_ntt(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, 
     if (fe_eq(fe_mont_pow_u64(root_m, n / 2), fe_mont_one())) return -3;
     const fe w_m = inverse ? fe_mont_inv(root_m) : root_m;
     const fe ninv_m = fe_mont_inv(fe_to_mont(fe_from_u64(n)));
-    const NttShape s = ntt_shape(log_n);
+    const fe scale_m = inverse ? ninv_m : fe_mont_one();
+    const NttShape s = ntt_shape(log_n, force3 != 0);
     TileArgs a;
     memset(&a, 0, sizeof(a));
-    fe cst1[8], cst2[8];
+    fe cst1[8], cst2[8], cst3[8];
+    if (s.l3 > 0) {
+        const size_t n1 = size_t(1) << s.l1, n2 = size_t(1) << s.l2, n3 = size_t(1) << s.l3, m = n2 * n3;
+        const fe w1_m = fe_mont_pow_u64(w_m, m);         // n1-point transforms over j1
+        const fe wsub_m = fe_mont_pow_u64(w_m, n1);      // root of the length-m sub-transforms
+        const fe w2_m = fe_mont_pow_u64(wsub_m, n3);     // n2-point transforms over j2
+        const fe w3_m = fe_mont_pow_u64(wsub_m, n2);     // n3-point transforms over j3
+        std::vector<fe> tw1 = pow_table(w1_m, fe_mont_one(), n1), tw2 = pow_table(w2_m, fe_mont_one(), n2),
+                        tw3 = pow_table(w3_m, fe_mont_one(), n3);
+        std::vector<fe> twb1 = twb_table(w_m, scale_m, n1, m), twb2 = twb_table(wsub_m, fe_mont_one(), n2, n3);
+        ntt_fill_cst(cst1, w1_m, (int)n1);
+        ntt_fill_cst(cst2, w2_m, (int)n2);
+        ntt_fill_cst(cst3, w3_m, (int)n3);
+        std::vector<fe> tmp(n * batch);
+        ntt_fill_3pass_a(a, (const fe *)in, (fe *)out, s, batch, tw1.data(), twb1.data(), cst1);
+        run_tiles_dyn(s.l1, a);
+        ntt_fill_3pass_b(a, (const fe *)out, tmp.data(), s, batch, tw2.data(), twb2.data(), cst2);
+        run_tiles_dyn(s.l2, a);
+        ntt_fill_3pass_c(a, tmp.data(), (fe *)out, s, batch, tw3.data(), cst3);
+        run_tiles_dyn(s.l3, a);
+        return 0;
+    }
     if (log_n <= 10) {
         std::vector<fe> tw1 = pow_table(w_m, fe_mont_one(), n);
         ntt_fill_cst(cst1, w_m, (int)n);
         std::vector<fe> tmp((const fe *)in, (const fe *)in + n * batch);
-        ntt_fill_single(a, tmp.data(), (fe *)out, log_n, batch, tw1.data(), cst1, inverse ? 1 : 0,
-                        inverse ? ninv_m : fe_mont_one());
+        ntt_fill_single(a, tmp.data(), (fe *)out, log_n, batch, tw1.data(), cst1, inverse ? 1 : 0, scale_m);
         run_tiles_dyn(log_n, a);
         return 0;
     }
     const size_t n1 = size_t(1) << s.l1, n2 = size_t(1) << s.l2;
     const fe w1_m = fe_mont_pow_u64(w_m, n2), w2_m = fe_mont_pow_u64(w_m, n1);
     std::vector<fe> tw1 = pow_table(w1_m, fe_mont_one(), n1), tw2 = pow_table(w2_m, fe_mont_one(), n2);
-    std::vector<fe> twb(n);
-    for (size_t k = 0; k < n1; k++) {
-        const fe wk = fe_mont_pow_u64(w_m, k);
-        fe acc = inverse ? ninv_m : fe_mont_one();
-        for (size_t j = 0; j < n2; j++) {
-            twb[k * n2 + j] = acc;
-            acc = fe_montmul(acc, wk);
-        }
-    }
+    std::vector<fe> twb = twb_table(w_m, scale_m, n1, n2);
     ntt_fill_cst(cst1, w1_m, (int)n1);
     ntt_fill_cst(cst2, w2_m, (int)n2);
     std::vector<fe> tmp(n * batch);
@@ -156,6 +184,9 @@ int emu_ntt(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, 
     ntt_fill_pass2(a, tmp.data(), (fe *)out, s, batch, tw2.data(), cst2);
     run_tiles_dyn(s.l2, a);
     return 0;
+}
+int emu_ntt(uint64_t *out, const uint64_t *in, int log_n, const uint64_t *root, int inverse, size_t batch) {
+    return emu_ntt_ex(out, in, log_n, root, inverse, batch, 0);
 }
 
 uint32_t emu_decimal(uint8_t *buf40, const uint64_t *x) {

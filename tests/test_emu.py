@@ -64,6 +64,30 @@ def test_tile_ntt_all_sizes(E, logn, shape):
                 assert (out[b * n:(b + 1) * n] == want).all(), (logn, inverse, batch, b)
 
 
+@pytest.mark.parametrize("shape", [(4, 8), (3, 4)])
+@pytest.mark.parametrize("logn", [3, 4, 6, 9, 12, 15])
+def test_three_pass_split_small(E, logn, shape):
+    """the n = n1*n2*n3 plan used above 2^20, forced at small sizes"""
+    E.emu_set_shape(*shape)
+    E.emu_ntt_ex.restype = ctypes.c_int
+    rng = random.Random(300 + logn)
+    n = 1 << logn
+    w = O.primitive_nth_root(n)
+    for inverse in (0, 1):
+        for batch in (1, 3):
+            x = O.to_np([rng.randrange(P) for _ in range(n * batch)])
+            out = np.zeros_like(x)
+            assert E.emu_ntt_ex(O._ptr(out), O._ptr(x), logn, O._ptr(O._fe(w)), inverse, ctypes.c_size_t(batch), 1) == 0
+            for b in range(batch):
+                xb = x[b * n:(b + 1) * n]
+                want = O.intt_np(w, xb) if inverse else O.ntt_np(w, xb)
+                assert (out[b * n:(b + 1) * n] == want).all(), (logn, inverse, batch, b)
+            # in place
+            y = x.copy()
+            assert E.emu_ntt_ex(O._ptr(y), O._ptr(y), logn, O._ptr(O._fe(w)), inverse, ctypes.c_size_t(batch), 1) == 0
+            assert (y == out).all()
+
+
 def test_tile_ntt_2_16_and_nonstandard_root(E):
     E.emu_set_shape(4, 8)
     rng = random.Random(9)

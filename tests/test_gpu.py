@@ -63,6 +63,33 @@ def test_ntt_matches_oracle(eng, log_n):
                 assert (got[b * n:(b + 1) * n] == want).all(), (log_n, batch, inverse, b)
 
 
+@pytest.mark.parametrize("log_n", [21, 22])
+def test_ntt_three_pass_matches_oracle(eng, log_n):
+    """above 2^20 the transform is a three-pass n1*n2*n3 split"""
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    x = rand_np(2000 + log_n, n)
+    vx = up(eng, x)
+    y = eng.ntt(vx, log_n, w)
+    assert (down(eng, y) == O.ntt_np(w, x, parallel=True)).all()
+    assert bool((eng.ntt(y, log_n, w, inverse=True) == vx).all())
+
+
+def test_ntt_2_24_roundtrip_in_place(eng):
+    log_n = 24
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    x = rand_np(24, n)
+    v = up(eng, x)
+    ref = v.clone()
+    assert eng.lib.sa_ntt(v.data_ptr(), v.data_ptr(), log_n, sa_engine._limbs(w), 0, 1, eng._stream()) == 0
+    assert not bool((v == ref).all())
+    assert eng.lib.sa_ntt(v.data_ptr(), v.data_ptr(), log_n, sa_engine._limbs(w), 1, 1, eng._stream()) == 0
+    assert bool((v == ref).all())
+    with pytest.raises(Exception):
+        eng.ntt(eng.empty(16), 27, w)
+
+
 def test_ntt_edge_inputs_and_roots(eng):
     for log_n in (3, 10, 13):
         n = 1 << log_n
