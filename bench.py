@@ -260,6 +260,20 @@ def run_ours(args):
         fri_cpu_ms = (time.perf_counter() - t0) * 1e3
         assert roots == oroots, "FRI commit roots differ from the oracle"
 
+    # ---- the Python list API of the drop-in (list[FieldElement] in and out), one 2^20 transform
+    list_api_s = None
+    if rank == 0 and world == 1:
+        import sa_host
+        import sa_marshal
+        import ntt as dropin_ntt
+        field = sa_host.algebra.Field.main()
+        FE = sa_host.algebra.FieldElement
+        vals = sa_marshal.unpack(x[:N].cpu().numpy(), field, FE)
+        t0 = time.perf_counter()
+        outl = dropin_ntt.ntt(FE(w, field), vals)
+        list_api_s = time.perf_counter() - t0
+        assert outl[12345].value == int(want[12345][0]) | (int(want[12345][1]) << 64)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -273,6 +287,11 @@ def run_ours(args):
     # roofline of the dominant kernel, ntt_tile_kernel<10>: two launches per step (column pass, row pass);
     # each launch reads and writes the whole batch once: 32 * n * BATCH algorithmic bytes
     launches_per_step = 2
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):  # dram bytes per launch from the committed ncu --set full capture
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch_mean")
     alg_bytes_per_launch = 32 * N * BATCH
     launch_s = ms_per_step * 1e-3 / launches_per_step
     achieved = alg_bytes_per_launch / launch_s / 1e9
@@ -284,9 +303,10 @@ def run_ours(args):
                    "l2": "inputs larger than L2: %d MiB in + %d MiB out per step" % (BATCH * 16, BATCH * 16),
                    "parallelism": "batch sharded across %d GPU(s), no collective in the timed region" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "ntt_tile_kernel<10>", "launches_per_step": launches_per_step,
+                     "traffic": traffic, "kernel": "ntt_tile_kernel<10>", "launches_per_step": launches_per_step,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
-                     "note": "integer-issue bound expected to bind first (SURVEY.md 8d); see profiles/"},
+                     "note": "bound by the integer pipes, not HBM: ~900 int instructions per element put the "
+                             "floor at ~31 us per 2^20 transform = frac 0.33 (DESIGN.md 3.2, profiles/r01_notes.md)"},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP); reference "
                                    "pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
@@ -295,6 +315,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "single_ntt_us": single_us,
+        "list_api_ntt_2_20_s": list_api_s,
         "fri_commit_ms_2_20": fri_ms, "fri_commit_cpu_port_ms_2_20": fri_cpu_ms,
     }
     print(json.dumps(line))

@@ -19,6 +19,7 @@ from algebra import FieldElement
 
 import sa_engine
 import sa_marshal
+import sa_accel  # noqa: F401  (opt-in Polynomial.__mul__ acceleration; inert unless enabled)
 
 _P = sa_engine.P
 

@@ -263,3 +263,31 @@ def case_merkle_class():
     root = F.Merkle.commit(data)
     for i in range(16):
         assert F.Merkle.verify(root, i, F.Merkle.open(i, data), data[i])
+
+
+# ----------------------------------------------------------------- sa_accel
+def case_accel_polymul():
+    """opt-in device Polynomial.__mul__ (section 8 f2) == the schoolbook product, same lengths"""
+    import sa_accel
+    rng = random.Random(77)
+
+    def rnd(n, zero_tail=0):
+        return T.Polynomial([T.fe(rng.randrange(P)) for _ in range(n)] + [T.field.zero()] * zero_tail)
+    shapes = [(1, 1), (40, 70), (64, 64), (100, 3, 5), (283, 283), (850, 28), (1, 3000), (1025, 1024, 2)]
+    pairs = []
+    for sh in shapes:
+        tail = sh[2] if len(sh) > 2 else 0
+        pairs.append((rnd(sh[0], tail), rnd(sh[1])))
+    want = [vals((a * b).coefficients) for a, b in pairs]
+    assert sa_accel._original_mul is None
+    sa_accel.enable(threshold=1)
+    try:
+        for (a, b), w in zip(pairs, want):
+            got = a * b
+            assert vals(got.coefficients) == w and len(got.coefficients) == len(a.coefficients) + len(b.coefficients) - 1
+        assert (T.Polynomial([]) * pairs[0][0]).coefficients == []
+        x = T.Polynomial([T.field.zero(), T.field.one()])
+        assert vals(((x ^ 5) * pairs[1][0]).coefficients) == [0] * 5 + vals(pairs[1][0].coefficients)
+    finally:
+        sa_accel.disable()
+    assert T.Polynomial.__mul__ is not sa_accel.device_mul

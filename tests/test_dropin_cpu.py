@@ -64,6 +64,10 @@ def test_merkle_class():
     C.case_merkle_class()
 
 
+def test_accel_polymul():
+    C.case_accel_polymul()
+
+
 def test_engine_use_is_recorded():
     """the drop-in really goes through the engine object (no hidden host arithmetic)"""
     eng = sa_engine.get_engine()
@@ -117,3 +121,7 @@ print(hashlib.sha256(proof).hexdigest(), len(proof), ok, len(sa_engine.get_engin
     g = load_golden("faststark_trace.json")
     assert out[0] == g["proof_sha256"] and int(out[1]) == g["proof_len"]
     assert out[2] == "True" and int(out[3]) > 10
+    # same again with the opt-in device Polynomial.__mul__ (section 8 f2): still the same bytes
+    env = dict(os.environ, SA_B200_ACCEL_POLYMUL="1")
+    out2 = subprocess.check_output([sys.executable, "-c", code], text=True, env=env).split()
+    assert out2[:3] == out[:3] and int(out2[3]) > int(out[3])

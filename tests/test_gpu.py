@@ -273,5 +273,9 @@ def test_dropin_merkle_class(eng):
     C.case_merkle_class()
 
 
+def test_dropin_accel_polymul(eng):
+    C.case_accel_polymul()
+
+
 def test_kernels_were_launched(eng):
     assert eng.launch_count() > 100
