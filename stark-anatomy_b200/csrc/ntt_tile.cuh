@@ -65,7 +65,11 @@ struct TilePlan {
     static constexpr int TPT = (L / E) * C;        // threads per tile
     static constexpr int TPC = TPT >= 128 ? 1 : 128 / TPT;  // tiles per CTA
     static constexpr int THREADS = TPT * TPC;
-    SA_HDC size_t smem_bytes() { return NST > 1 ? (size_t)TPC * L * C * sizeof(fe) : 0; }
+    // dynamic shared memory: the tile rows, then the stage-twiddle table (L elements, staged by one
+    // bulk-async copy, see tile_stage_twiddles), then the 8-byte mbarrier it completes on
+    static constexpr size_t TILE_BYTES = (size_t)TPC * L * C * sizeof(fe);
+    static constexpr size_t TW_BYTES = (size_t)L * sizeof(fe);
+    SA_HDC size_t smem_bytes() { return NST > 1 ? TILE_BYTES + TW_BYTES + 16 : 0; }
 };
 
 SA_HDC int tile_bitrev(int i, int r) {
@@ -162,9 +166,41 @@ SA_HD long long tile_batch_offset(long long b, int inner, long long sb, long lon
 
 // A full-radix (E-point) stage that is NOT the last stage: one unit per thread.
 //   ml = log2 M of this stage (run-time, so all such stages share one copy of the code)
+#if defined(__CUDA_ARCH__)
+// TMA-style staging of the per-stage twiddle table: one thread arms an mbarrier with the byte count
+// and issues a single bulk-async copy global -> shared (SASS: UBLKCP); everybody waits on the
+// barrier's phase right before the first twiddle is needed, so the copy overlaps the first block's
+// global loads and register transform.
+__device__ __forceinline__ void tile_stage_twiddles(fe *dst, const fe *src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                 "l"(src), "r"(bytes), "r"(bar_a)
+                 : "memory");
+}
+__device__ __forceinline__ void tile_wait_twiddles(uint64_t *bar) {
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TW_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra TW_DONE_%=;\n\t"
+        "bra TW_WAIT_%=;\n\t"
+        "TW_DONE_%=:\n\t"
+        "}" ::"r"(bar_a)
+        : "memory");
+}
+#endif
+
+//   tw  = the stage-twiddle table (shared memory on the device, see tile_stage_twiddles)
+//   bar = its mbarrier (device) / nullptr (host emulation)
 template <int LOGL, int ELOG, int C, int FLAGS>
 SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid, bool first,
-                               int ml) {
+                               int ml, const fe *tw, uint64_t *bar) {
     using P = TilePlan<LOGL, ELOG, C>;
     constexpr int R = P::E;
     constexpr int CSTEP = 16 / R;  // a non-last stage exists only when L > E >= 8, so cst = w_16^k
@@ -190,13 +226,18 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
         for (int d = 0; d < R; d++) x[d] = tile_ld(sm + (row0 + d * M) * C + c);
     }
     dft_regs<R>(x, a.cst, CSTEP);
+#if defined(__CUDA_ARCH__)
+    if (first) tile_wait_twiddles(bar);  // the bulk copy has had the loads and the transform to land
+#else
+    (void)bar;
+#endif
     // multiply output k by w_{M*R}^(k*m) = w_L^((k*m) << wlog), then park it in row row0 + k*M
     tile_st(sm + row0 * C + c, x[0]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int k = 1; k < R; k++) {
-        const fe w = tile_ldg(a.tw + ((k * m) << wlog));
+        const fe w = tile_ld(tw + ((k * m) << wlog));
         tile_st(sm + (row0 + k * M) * C + c, fe_montmul(x[k], w));
     }
 }
@@ -254,8 +295,10 @@ template <int LOGL, int ELOG, int C, int FLAGS = TF_DYNAMIC>
 struct TileStages {
     using P = TilePlan<LOGL, ELOG, C>;
     // stage index st < NLOOP -> full stage with ml = LOGL - (st + 1) * EL
-    SA_HD static void full(int st, int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
-        ntt_tile_full_stage<LOGL, ELOG, C, FLAGS>(t, sm, a, b, col0, valid, st == 0, LOGL - (st + 1) * P::EL);
+    SA_HD static void full(int st, int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid,
+                           const fe *tw, uint64_t *bar) {
+        ntt_tile_full_stage<LOGL, ELOG, C, FLAGS>(t, sm, a, b, col0, valid, st == 0, LOGL - (st + 1) * P::EL, tw,
+                                                   bar);
     }
     SA_HD static void last(int t, fe *sm, const TileArgs &a, long long b, int col0, bool valid) {
         ntt_tile_last_stage<LOGL, ELOG, C, FLAGS>(t, sm, a, b, col0, valid);

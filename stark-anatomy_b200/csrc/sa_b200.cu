@@ -80,9 +80,18 @@ __global__ void __launch_bounds__(TilePlan<LOGL, ELOG, C>::THREADS, TileLaunch<L
     const long long b = valid ? tile / tiles_per_batch : 0;
     const int col0 = valid ? (int)(tile % tiles_per_batch) * C : 0;
     fe *sm = smem + (size_t)tic * P::L * C;
+    fe *tw = nullptr;
+    uint64_t *bar = nullptr;
+    if constexpr (P::NLOOP > 0) {
+        // stage the twiddle table of this tile length into shared memory (bulk-async copy + mbarrier)
+        tw = smem + P::TILE_BYTES / sizeof(fe);
+        bar = reinterpret_cast<uint64_t *>(tw + P::L);
+        if (threadIdx.x == 0) tile_stage_twiddles(tw, a.tw, (uint32_t)P::TW_BYTES, bar);
+        __syncthreads();  // the barrier is initialised before anybody polls it
+    }
 #pragma unroll 1
     for (int st = 0; st < P::NLOOP; st++) {
-        S::full(st, t, sm, a, b, col0, valid);
+        S::full(st, t, sm, a, b, col0, valid, tw, bar);
         __syncthreads();
     }
     S::last(t, sm, a, b, col0, valid);

@@ -36,7 +36,7 @@ static void run_tiles_variant(const TileArgs &a) {
         const int col0 = (int)(tile % tiles_per_batch) * C;
         // each loop over t is one barrier phase of the CTA
         for (int st = 0; st < P::NLOOP; st++)
-            for (int t = 0; t < P::TPT; t++) S::full(st, t, sm.data(), a, b, col0, true);
+            for (int t = 0; t < P::TPT; t++) S::full(st, t, sm.data(), a, b, col0, true, a.tw, nullptr);
         for (int t = 0; t < P::TPT; t++) S::last(t, sm.data(), a, b, col0, true);
     }
 }
