@@ -72,6 +72,11 @@ struct TilePlan {
     SA_HDC size_t smem_bytes() { return NST > 1 ? TILE_BYTES + TW_BYTES + 16 : 0; }
 };
 
+// slot of w^e in the stage-twiddle table: the low three bits are XORed with the next three, so the
+// strided look-ups of the middle stages ((k*m) << 3: all multiples of 8) spread over the eight
+// 16-byte bank groups of shared memory instead of piling onto one
+SA_HDC int tile_tw_slot(int e) { return e ^ ((e >> 3) & 7); }
+
 SA_HDC int tile_bitrev(int i, int r) {
     int j = 0;
     for (int b = 1, bb = r >> 1; b < r; b <<= 1, bb >>= 1)
@@ -227,7 +232,12 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
     }
     dft_regs<R>(x, a.cst, CSTEP);
 #if defined(__CUDA_ARCH__)
-    if (first) tile_wait_twiddles(bar);  // the bulk copy has had the loads and the transform to land
+    // table and barrier sit at fixed offsets of the dynamic shared memory window: address them from
+    // the window base (immediate offsets) instead of keeping two more pointers live across the loop
+    extern __shared__ uint4 sa_smem_u4[];
+    tw = reinterpret_cast<const fe *>(sa_smem_u4) + P::TILE_BYTES / sizeof(fe);
+    if (first) tile_wait_twiddles(reinterpret_cast<uint64_t *>(const_cast<fe *>(tw) + P::L));
+    (void)bar;
 #else
     (void)bar;
 #endif
@@ -237,7 +247,7 @@ SA_HD void ntt_tile_full_stage(int t, fe *sm, const TileArgs &a, long long b, in
 #pragma unroll
 #endif
     for (int k = 1; k < R; k++) {
-        const fe w = tile_ld(tw + ((k * m) << wlog));
+        const fe w = tile_ld(tw + tile_tw_slot((k * m) << wlog));
         tile_st(sm + (row0 + k * M) * C + c, fe_montmul(x[k], w));
     }
 }

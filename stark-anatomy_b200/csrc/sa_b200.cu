@@ -97,13 +97,16 @@ __global__ void __launch_bounds__(TilePlan<LOGL, ELOG, C>::THREADS, TileLaunch<L
     S::last(t, sm, a, b, col0, valid);
 }
 
-// out[e] = base^e * lead (Montgomery form) for e < count; 16 consecutive powers per thread
-__global__ void k_pow_table(fe *out, fe base_m, fe lead_m, long long count) {
+// out[slot(e)] = base^e * lead (Montgomery form) for e < count; 16 consecutive powers per thread.
+// swz != 0 stores in the bank-spreading order of tile_tw_slot (stage-twiddle tables, count % 64 == 0
+// or count < 8 so the permutation stays inside the table).
+__global__ void k_pow_table(fe *out, fe base_m, fe lead_m, long long count, int swz) {
     const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (e0 >= count) return;
     fe acc = fe_montmul(fe_mont_pow_u64(base_m, (uint64_t)e0), lead_m);
     for (int i = 0; i < 16 && e0 + i < count; i++) {
-        tile_st(out + e0 + i, acc);
+        const long long e = e0 + i;
+        tile_st(out + (swz ? (long long)tile_tw_slot((int)e) : e), acc);
         acc = fe_montmul(acc, base_m);
     }
 }
@@ -425,11 +428,12 @@ using PlanKey = std::tuple<int, int, uint64_t, uint64_t, int>;  // device, log_n
 static std::mutex g_plan_mu;
 static std::map<PlanKey, NttPlan> g_plans;
 
-static int build_pow_table(fe **out, const fe &base_m, const fe &lead_m, long long count, cudaStream_t st) {
+static int build_pow_table(fe **out, const fe &base_m, const fe &lead_m, long long count, cudaStream_t st,
+                           int swz = 0) {
     SA_CUDA(cudaMalloc(out, sizeof(fe) * (size_t)count));
     const long long threads = (count + 15) / 16;
     const int bs = 128;
-    k_pow_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(*out, base_m, lead_m, count);
+    k_pow_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(*out, base_m, lead_m, count, swz);
     SA_LAUNCH_CHECK();
     return SA_OK;
 }
@@ -468,9 +472,9 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         const fe wsub_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-m sub-transforms
         const fe w2_m = fe_mont_pow_u64(wsub_m, (uint64_t)n3);
         const fe w3_m = fe_mont_pow_u64(wsub_m, (uint64_t)n2);
-        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw3, w3_m, fe_mont_one(), n3, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw3, w3_m, fe_mont_one(), n3, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w1_m, n1);
         ntt_fill_cst(p.cst2, w2_m, n2);
         ntt_fill_cst(p.cst3, w3_m, n3);
@@ -485,7 +489,7 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(p.twb2, wsub_m, fe_mont_one(), n2, n3);
         SA_LAUNCH_CHECK();
     } else if (log_n <= 10) {
-        if ((rc = build_pow_table(&p.tw1, w_m, fe_mont_one(), (long long)n, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw1, w_m, fe_mont_one(), (long long)n, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w_m, (int)n);
         p.has_scale = inverse ? 1 : 0;
         p.scale_m = inverse ? ninv_m : fe_mont_one();
@@ -493,8 +497,8 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         const int n1 = 1 << p.l1, n2 = 1 << p.l2;
         const fe w1_m = fe_mont_pow_u64(w_m, (uint64_t)n2);  // root of the length-n1 column transforms
         const fe w2_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-n2 row transforms
-        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w1_m, n1);
         ntt_fill_cst(p.cst2, w2_m, n2);
         SA_CUDA(cudaMalloc(&p.twb, sizeof(fe) * (size_t)n));
@@ -559,9 +563,10 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
         if (g_tile_elog == 4 && g_tile_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
     }
 #endif
-    // measured on B200 (profiles/r01_tile_shapes.md): 8-element register blocks (64 registers,
-    // 32 warps/SM) with 4-column tiles win for the big tiles; small tiles keep 16-element blocks
-    if (LOGL >= 9) return launch_tile<LOGL, 3, 4>(a, st);
+    // measured on B200 (profiles/r01_notes.md, r01e_tile_shapes_tma_twiddles.jsonl): with the stage
+    // twiddles in shared memory, 16-element register blocks on 4-column tiles (2 CTAs x 256 threads
+    // per SM) win for the big tiles
+    if (LOGL >= 9) return launch_tile<LOGL, 4, 4>(a, st);
     return launch_tile<LOGL, 4, 8>(a, st);
 }
 static int launch_tile_dyn(int logl, const TileArgs &a, cudaStream_t st) {

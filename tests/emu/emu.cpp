@@ -73,11 +73,12 @@ static void run_tiles_dyn(int logl, const TileArgs &a) {
         case 10: run_tiles_shape<10>(a); break;
     }
 }
-static std::vector<fe> pow_table(const fe &base_m, const fe &lead_m, size_t count) {
+// swz: stage-twiddle tables are stored in tile_tw_slot order (see k_pow_table in sa_b200.cu)
+static std::vector<fe> pow_table(const fe &base_m, const fe &lead_m, size_t count, bool swz = true) {
     std::vector<fe> t(count);
     fe acc = lead_m;
     for (size_t i = 0; i < count; i++) {
-        t[i] = acc;
+        t[swz ? (size_t)tile_tw_slot((int)i) : i] = acc;
         acc = fe_montmul(acc, base_m);
     }
     return t;
@@ -252,7 +253,7 @@ int emu_fri_round(uint64_t *next, uint8_t *next_tree, const uint64_t *cw, size_t
                   const uint64_t *offset, const uint64_t *omega) {
     memset(next_tree, 0, 64);
     const fe winv_m = fe_mont_inv(fe_to_mont(from_limbs(omega)));
-    std::vector<fe> xinv = pow_table(winv_m, fe_mont_one(), n / 2);
+    std::vector<fe> xinv = pow_table(winv_m, fe_mont_one(), n / 2, false);
     MerkleArgs a;
     memset(&a, 0, sizeof(a));
     a.tree = (uint64_t *)next_tree;
