@@ -203,4 +203,93 @@ SA_HD void merkle_node_digest(uint64_t out[8], const uint64_t left[8], const uin
     blake2b_single_block(out, m, 128u);
 }
 
+// ---- four lanes per compression (latency-bound upper tree levels) ----------------------------
+// The 4x4 state is split by columns: lane j of a quad holds (a, b, c, d) = (v[j], v[4+j], v[8+j],
+// v[12+j]).  A round is the column G on the lane's own column, a rotation of b, c, d by 1, 2, 3
+// lanes (which puts the diagonals in the lanes), the diagonal G, and the rotation back.  The
+// message words are read from `msg` (16 contiguous words = left || right child digests, in shared
+// memory on the device) by index, so no lane needs all sixteen in registers.  The dependent chain
+// per compression is the same 24 G steps, but a warp that has only a few nodes left to hash keeps
+// all its lanes busy and issues a quarter of the instructions per node.
+// sigma rows packed as sixteen nibbles, nibble i = sigma[r][i]
+SA_HD uint64_t b2_sigma_packed(int r) {
+    const uint64_t s[10] = {0xfedcba9876543210ULL, 0x357b20c16df984aeULL, 0x491763eadf250c8bULL,
+                            0x8f04a562ebcd1397ULL, 0xd386cb1efa427509ULL, 0x91ef57d438b0a6c2ULL,
+                            0xb8293670a4def15cULL, 0xa2684f05931ce7bdULL, 0x5a417d2c803b9ef6ULL,
+                            0x0dc3e9bf5167482aULL};
+    return s[r % 10];
+}
+SA_HD void b2_coop4_init(int j, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d, uint32_t len) {
+    const uint64_t iv[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL,
+                            0xa54ff53a5f1d36f1ULL, 0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL,
+                            0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    a = iv[j] ^ (j == 0 ? 0x01010040ULL : 0);
+    b = iv[4 + j];
+    c = iv[j];
+    d = iv[4 + j];
+    if (j == 0) d ^= (uint64_t)len;
+    if (j == 2) d = ~d;
+}
+// one G on the lane's current (a, b, c, d) with message words x, y
+SA_HD void b2_coop4_g(uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d, uint64_t x, uint64_t y) {
+    SA_B2_G(a, b, c, d, x, y);
+}
+// the two digest words lane j ends up with: out[j] and out[4 + j]
+SA_HD void b2_coop4_final(int j, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t &lo, uint64_t &hi) {
+    const uint64_t iv[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL,
+                            0xa54ff53a5f1d36f1ULL, 0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL,
+                            0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    lo = (iv[j] ^ (j == 0 ? 0x01010040ULL : 0)) ^ a ^ c;
+    hi = iv[4 + j] ^ b ^ d;
+}
+
+#if defined(__CUDACC__)
+// device: all 32 lanes of the warp call this together; lane j = threadIdx.x & 3 of each quad
+__device__ __forceinline__ void blake2b_coop4_node(uint64_t &out_lo, uint64_t &out_hi, const uint64_t *msg, int j) {
+    uint64_t a, b, c, d;
+    b2_coop4_init(j, a, b, c, d, 128u);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        const uint64_t sg = b2_sigma_packed(r) >> (8 * j);
+        b2_coop4_g(a, b, c, d, msg[sg & 15], msg[(sg >> 4) & 15]);
+        b = __shfl_sync(0xffffffffu, b, (j + 1) & 3, 4);
+        c = __shfl_sync(0xffffffffu, c, (j + 2) & 3, 4);
+        d = __shfl_sync(0xffffffffu, d, (j + 3) & 3, 4);
+        b2_coop4_g(a, b, c, d, msg[(sg >> 32) & 15], msg[(sg >> 36) & 15]);
+        b = __shfl_sync(0xffffffffu, b, (j + 3) & 3, 4);
+        c = __shfl_sync(0xffffffffu, c, (j + 2) & 3, 4);
+        d = __shfl_sync(0xffffffffu, d, (j + 1) & 3, 4);
+    }
+    b2_coop4_final(j, a, b, c, d, out_lo, out_hi);
+}
+#endif
+// host model of the same four-lane schedule (tests/emu): out = blake2b(msg[0..16))
+inline void blake2b_coop4_node_host(uint64_t out[8], const uint64_t msg[16]) {
+    uint64_t a[4], b[4], c[4], d[4], t[4];
+    for (int j = 0; j < 4; j++) b2_coop4_init(j, a[j], b[j], c[j], d[j], 128u);
+    for (int r = 0; r < 12; r++) {
+        for (int j = 0; j < 4; j++) {
+            const uint64_t sg = b2_sigma_packed(r) >> (8 * j);
+            b2_coop4_g(a[j], b[j], c[j], d[j], msg[sg & 15], msg[(sg >> 4) & 15]);
+        }
+        for (int j = 0; j < 4; j++) t[j] = b[(j + 1) & 3];
+        for (int j = 0; j < 4; j++) b[j] = t[j];
+        for (int j = 0; j < 4; j++) t[j] = c[(j + 2) & 3];
+        for (int j = 0; j < 4; j++) c[j] = t[j];
+        for (int j = 0; j < 4; j++) t[j] = d[(j + 3) & 3];
+        for (int j = 0; j < 4; j++) d[j] = t[j];
+        for (int j = 0; j < 4; j++) {
+            const uint64_t sg = b2_sigma_packed(r) >> (8 * j);
+            b2_coop4_g(a[j], b[j], c[j], d[j], msg[(sg >> 32) & 15], msg[(sg >> 36) & 15]);
+        }
+        for (int j = 0; j < 4; j++) t[j] = b[(j + 3) & 3];
+        for (int j = 0; j < 4; j++) b[j] = t[j];
+        for (int j = 0; j < 4; j++) t[j] = c[(j + 2) & 3];
+        for (int j = 0; j < 4; j++) c[j] = t[j];
+        for (int j = 0; j < 4; j++) t[j] = d[(j + 1) & 3];
+        for (int j = 0; j < 4; j++) d[j] = t[j];
+    }
+    for (int j = 0; j < 4; j++) b2_coop4_final(j, a[j], b[j], c[j], d[j], out[j], out[4 + j]);
+}
+
 }  // namespace sa

@@ -283,15 +283,30 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
     long long base = (a.width + blk * a.chunk) >> a.ipt_log;
     for (int wl = active / 2; wl >= 1; wl >>= 1) {
         base >>= 1;
-        const bool mine = tid < wl;
-        if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
-        __syncthreads();
-        if (mine) {
-            uint64_t *node = a.tree + (base + tid) * 8;
+        if (wl > MK_THREADS / 4) {  // plenty of nodes: one thread per node
+            const bool mine = tid < wl;
+            if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
+            __syncthreads();
+            if (mine) {
+                uint64_t *node = a.tree + (base + tid) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                sm[tid * 8 + i] = d[i];
-                node[i] = d[i];
+                for (int i = 0; i < 8; i++) {
+                    sm[tid * 8 + i] = d[i];
+                    node[i] = d[i];
+                }
+            }
+        } else {  // few nodes, the level is a dependency chain: four lanes per node (hash.cuh)
+            const int q = tid >> 2, j = tid & 3;
+            const bool warp_on = (tid >> 5) < ((4 * wl + 31) >> 5);  // whole warps only (shuffles)
+            uint64_t lo = 0, hi = 0;
+            if (warp_on) blake2b_coop4_node(lo, hi, sm + (2 * (q < wl ? q : 0)) * 8, j);
+            __syncthreads();
+            if (warp_on && q < wl) {
+                uint64_t *node = a.tree + (base + q) * 8;
+                sm[q * 8 + j] = lo;
+                sm[q * 8 + 4 + j] = hi;
+                node[j] = lo;
+                node[4 + j] = hi;
             }
         }
         __syncthreads();

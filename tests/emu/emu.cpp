@@ -201,6 +201,13 @@ void emu_leaf_digest(uint8_t *out64, const uint64_t *x) {
     merkle_leaf_digest(d, from_limbs(x));
     memcpy(out64, d, 64);
 }
+void emu_node_digest_coop4(uint8_t *out64, const uint8_t *left, const uint8_t *right) {
+    uint64_t m[16], d[8];
+    memcpy(m, left, 64);
+    memcpy(m + 8, right, 64);
+    blake2b_coop4_node_host(d, m);
+    memcpy(out64, d, 64);
+}
 void emu_node_digest(uint8_t *out64, const uint8_t *left, const uint8_t *right) {
     uint64_t l[8], r[8], d[8];
     memcpy(l, left, 64);
@@ -223,9 +230,13 @@ static void emu_merkle_reduce(MerkleArgs a) {
             for (int wl = active / 2; wl >= 1; wl >>= 1) {
                 base >>= 1;
                 std::vector<uint64_t> regs((size_t)wl * 8);
-                for (int tid = 0; tid < wl; tid++)  // phase 1: read children, hash
-                    merkle_node_digest(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8],
-                                       &sm[(size_t)(2 * tid + 1) * 8]);
+                for (int tid = 0; tid < wl; tid++) {  // phase 1: read children, hash
+                    if (wl > MK_THREADS / 4)
+                        merkle_node_digest(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8],
+                                           &sm[(size_t)(2 * tid + 1) * 8]);
+                    else  // the four-lanes-per-node schedule of the small levels
+                        blake2b_coop4_node_host(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8]);
+                }
                 for (int tid = 0; tid < wl; tid++)  // phase 2: publish
                     for (int i = 0; i < 8; i++) {
                         sm[(size_t)tid * 8 + i] = regs[(size_t)tid * 8 + i];

@@ -120,6 +120,8 @@ def test_decimal_and_leaf(E):
         d = np.zeros(64, dtype=np.uint8)
         E.emu_node_digest(O._ptr(d), O._ptr(np.frombuffer(l, dtype=np.uint8)), O._ptr(np.frombuffer(r, dtype=np.uint8)))
         assert d.tobytes() == hashlib.blake2b(l + r).digest()
+        E.emu_node_digest_coop4(O._ptr(d), O._ptr(np.frombuffer(l, dtype=np.uint8)), O._ptr(np.frombuffer(r, dtype=np.uint8)))
+        assert d.tobytes() == hashlib.blake2b(l + r).digest()  # four-lanes-per-node schedule
 
 
 @pytest.mark.parametrize("logn", [0, 1, 2, 5, 8, 9, 10, 11, 12, 15, 16])
