@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -963,6 +964,9 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
     uint8_t *tree = (uint8_t *)trees;
     size_t len = n;
     int rc;
+    static const bool trace = getenv("SA_FRI_TRACE") != nullptr;  // per-round host timeline on stderr
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
     for (int r = 0; r < rounds; r++) {
         if (r == 0) {
             MerkleArgs a;
@@ -973,11 +977,19 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
             a.values = cur;
             if ((rc = merkle_reduce(a, st)) != SA_OK) return rc;
         }
+        const double t_launched = now();
         SA_CUDA(cudaMemcpyAsync(root_pinned, tree + 64, 64, cudaMemcpyDeviceToHost, st));
         SA_CUDA(cudaStreamSynchronize(st));
+        const double t_synced = now();
         uint64_t alpha[2] = {0, 0};
         const int want = r != rounds - 1;
         if (challenge(user, r, root_pinned, alpha, want) != 0) return SA_ECALLBACK;
+        if (trace) {
+            const double t_cb = now();
+            fprintf(stderr, "sa_fri_commit round %2d len %8zu: launch %.1f us, wait %.1f us, callback %.1f us\n", r, len,
+                    t_launched - t_mark, t_synced - t_launched, t_cb - t_synced);
+            t_mark = t_cb;
+        }
         if (!want) break;
         // fold layer r into layer r+1 and build its tree, one fused kernel (+ upper-level launches)
         fe *xinv = nullptr;
