@@ -291,3 +291,69 @@ def case_accel_polymul():
     finally:
         sa_accel.disable()
     assert T.Polynomial.__mul__ is not sa_accel.device_mul
+
+
+# ------------------------------------------- the reference's own test strategy
+def case_reference_style_properties(trials=5):
+    """Randomised cross-checks in the style of code/test_ntt.py, code/test_merkle.py (fresh
+    os.urandom inputs every run; fast path == slow path of the host value types)."""
+    import os
+    field = T.field
+
+    def sample(nbytes=17):
+        return field.sample(os.urandom(nbytes))
+
+    # test_ntt.py:6-19  ntt == evaluation on the powers of the root
+    n = 1 << 8
+    w = field.primitive_nth_root(n)
+    coeffs = [sample() for _ in range(n)]
+    assert N.ntt(w, coeffs) == T.Polynomial(coeffs).evaluate_domain([w ^ i for i in range(n)])
+    # test_ntt.py:21-32  intt(ntt(x)) == x
+    n = 1 << 7
+    w = field.primitive_nth_root(n)
+    values = [sample(1) for _ in range(n)]
+    assert N.intt(w, N.ntt(w, values)) == values
+    # test_ntt.py:34-70  multiply == schoolbook, divide recovers the factor
+    n = 1 << 6
+    w = field.primitive_nth_root(n)
+    for _ in range(trials):
+        lhs = T.Polynomial([sample() for _ in range(os.urandom(1)[0] % (n // 2) + 1)])
+        rhs = T.Polynomial([sample() for _ in range(os.urandom(1)[0] % (n // 2) + 1)])
+        product = N.fast_multiply(lhs, rhs, w, n)
+        assert product == lhs * rhs
+        if not lhs.is_zero() and not rhs.is_zero():
+            assert N.fast_coset_divide(product, lhs, field.generator(), w, n) == rhs
+    # test_ntt.py:72-96  fast_evaluate(fast_interpolate(domain, values), domain) == values
+    n = 1 << 9
+    w = field.primitive_nth_root(n)
+    for _ in range(2):
+        k = int.from_bytes(os.urandom(2), "big") % 200 + 1
+        seen, domain = set(), []
+        while len(domain) < k:
+            d = sample()
+            if d.value not in seen:
+                seen.add(d.value)
+                domain.append(d)
+        vals_ = [sample() for _ in range(k)]
+        poly = N.fast_interpolate(domain, vals_, w, n)
+        assert N.fast_evaluate(poly, domain, w, n) == vals_
+        assert N.fast_evaluate(N.fast_zerofier(domain, w, n), domain, w, n) == [field.zero()] * k
+    # test_ntt.py:98-116  coset evaluation == pointwise evaluation on offset * <omega>
+    n = 1 << 5
+    w = field.primitive_nth_root(n)
+    poly = T.Polynomial([sample() for _ in range(n // 2)])
+    got = N.fast_coset_evaluate(poly, field.generator(), w, n)
+    assert got == [poly.evaluate(field.generator() * (w ^ i)) for i in range(n)]
+    # test_merkle.py:4-47 with field-element leaves: every index opens and verifies; tampering fails
+    n = 64
+    data = [sample() for _ in range(n)]
+    root = F.Merkle.commit(data)
+    for i in range(n):
+        path = F.Merkle.open(i, data)
+        assert F.Merkle.verify(root, i, path, data[i])
+        assert not F.Merkle.verify(root, i, path, sample())           # wrong leaf
+        assert not F.Merkle.verify(root, (i + 1) % n, path, data[i])  # wrong index
+        bad = list(path)
+        bad[os.urandom(1)[0] % len(bad)] = os.urandom(64)
+        assert not F.Merkle.verify(root, i, bad, data[i])             # wrong path element
+    assert not F.Merkle.verify(os.urandom(64), 0, F.Merkle.open(0, data), data[0])  # wrong root

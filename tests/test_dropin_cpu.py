@@ -68,6 +68,10 @@ def test_accel_polymul():
     C.case_accel_polymul()
 
 
+def test_reference_style_properties():
+    C.case_reference_style_properties()
+
+
 def test_engine_use_is_recorded():
     """the drop-in really goes through the engine object (no hidden host arithmetic)"""
     eng = sa_engine.get_engine()

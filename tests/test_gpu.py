@@ -277,5 +277,9 @@ def test_dropin_accel_polymul(eng):
     C.case_accel_polymul()
 
 
+def test_dropin_reference_style_properties(eng):
+    C.case_reference_style_properties(trials=20)
+
+
 def test_kernels_were_launched(eng):
     assert eng.launch_count() > 100
