@@ -66,3 +66,32 @@ def all_gather_vectors(local, ranges, n, group=None):
     pieces = [out[r * longest:r * longest + (hi - lo) * n] for r, (lo, hi) in enumerate(ranges)]
     full = torch.cat(pieces, dim=0)
     return full if is_torch else full.numpy().view(np.uint64)
+
+
+def sharded_merkle_roots(vectors, n, group=None):
+    """Merkle roots (code/merkle.py:13-14) of a batch of B independent n-element codewords, B split
+    across the ranks; the 64-byte roots are all-gathered (B * 64 bytes in total).  Returns list[bytes]."""
+    import torch
+    eng = sa_engine.get_engine()
+    dist = _dist()
+    batch = eng.length(vectors) // n
+    rank = dist.get_rank(group) if dist else 0
+    world = dist.get_world_size(group) if dist else 1
+    lo, hi = shard_range(batch, rank, world)
+    mine = [eng.tree_root(eng.merkle_tree(eng.slice(vectors, b * n, (b + 1) * n))) for b in range(lo, hi)]
+    if world == 1:
+        return mine
+    longest = max(h - l for l, h in (shard_range(batch, r, world) for r in range(world)))
+    buf = torch.zeros((longest, 64), dtype=torch.uint8)
+    for i, r in enumerate(mine):
+        buf[i] = torch.frombuffer(bytearray(r), dtype=torch.uint8)
+    on_gpu = isinstance(vectors, torch.Tensor) and vectors.is_cuda
+    if on_gpu:
+        buf = buf.to(vectors.device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    roots = []
+    for r in range(world):
+        l, h = shard_range(batch, r, world)
+        roots += [bytes(parts[r][i].cpu().numpy().tobytes()) for i in range(h - l)]
+    return roots

@@ -41,6 +41,8 @@ def _worker(rank, world, port, batch, log_n, q):
     ok = bool((full == want).all()) and bool((local == want[lo * n:hi * n]).all())
     back = sa_dist.sharded_ntt(full, log_n, w, inverse=True)
     ok = ok and bool((back == x).all())
+    roots = sa_dist.sharded_merkle_roots(x, n)
+    ok = ok and roots == [O.merkle_root_np(x[b * n:(b + 1) * n]) for b in range(batch)]
     q.put((rank, ok, sa_engine.get_engine().calls[0]))
     dist.destroy_process_group()
 
