@@ -137,8 +137,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 during the run
+    # (NCCL's version banner, library chatter) is pointed at stderr, the line goes to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = sa_engine.get_engine()
@@ -159,6 +163,7 @@ def run_ours(args):
     x = torch.stack([lo, hi], dim=1).contiguous()  # hi limb < 2^63 < p's top limb: canonical
     y = torch.empty_like(x)
     import oracle as O
+    O.lib().so_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     w = O.primitive_nth_root(N)
     root = sa_engine._limbs(w)
     stream = torch.cuda.current_stream()
@@ -324,7 +329,8 @@ def run_ours(args):
         "list_api_ntt_2_20_s": list_api_s, "list_api_fri_commit_2_20_s": fri_list_api_s,
         "fri_commit_ms_2_20": fri_ms, "fri_commit_cpu_port_ms_2_20": fri_cpu_ms,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
