@@ -204,6 +204,16 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * BATCH * BUTTERFLIES_PER_NTT * args.steps / (ms * 1e-3)
 
+    # ---- the chip's measured 128-bit butterfly rate (montmul + add + sub on registers, no memory):
+    #      the compute roof this kernel actually lives under (profiles/r01_notes.md)
+    int_peak = None
+    if rank == 0:
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        iters, ilp, blocks, threads = 2000, 4, sms * 4, 256
+        mb_ms = lib.sa_microbench(3, ilp, iters, blocks, threads)
+        if mb_ms > 0:
+            int_peak = iters * ilp * blocks * threads / (mb_ms * 1e-3)
+
     # ---- single-transform latency (device resident), for the record
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 50
@@ -318,6 +328,11 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
                      "note": "bound by the integer pipes, not HBM: ~900 int instructions per element put the "
                              "floor at ~31 us per 2^20 transform = frac 0.33 (DESIGN.md 3.2, profiles/r01_notes.md)"},
+        "int_roofline": {"bound": "integer pipes (IMAD.WIDE / IADD3)", "achieved": value / world,
+                         "peak": int_peak, "unit": "butterflies/s per GPU",
+                         "frac": (value / world / int_peak) if int_peak else None,
+                         "how": "peak = sa_microbench: register-resident montmul+add+sub loop, 4 independent "
+                                "chains per thread, 1024 threads per SM, measured in this run"},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP); reference "
                                    "pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
