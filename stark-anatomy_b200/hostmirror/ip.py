@@ -46,6 +46,3 @@ class ProofStream:
         fresh = ProofStream()
         fresh.objects = pickle.loads(bb)
         return fresh
-
-    def __len__(self):
-        return len(self.objects)
