@@ -124,6 +124,36 @@ def test_ntt_in_place_and_host_entry(eng):
     torch.cuda.synchronize()
 
 
+def test_ntt_two_streams_and_threads(eng):
+    """independent work on two CUDA streams from two host threads (per-stream workspaces, shared
+    plan cache behind a mutex): results equal the oracle's"""
+    import threading
+    import torch
+    log_n, batch = 16, 4
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    xs = [rand_np(900 + i, n * batch) for i in range(2)]
+    outs = [None, None]
+
+    def work(i):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            v = up(eng, xs[i])
+            for _ in range(20):  # keep both streams busy at the same time
+                y = eng.ntt(v, log_n, w, batch=batch)
+                v = eng.ntt(y, log_n, w, inverse=True, batch=batch)
+            outs[i] = down(eng, eng.ntt(v, log_n, w, batch=batch))
+        st.synchronize()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(2):
+        want = O.ntt_batch_np(w, xs[i].reshape(batch, n, 2)).reshape(-1, 2)
+        assert (outs[i] == want).all()
+
+
 def test_ntt_2_20_golden_digest_and_roundtrip(eng):
     C.case_ntt_digests(1 << 20)
 
