@@ -524,6 +524,9 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
             p.twb, w_m, inverse ? ninv_m : fe_mont_one(), n1, n2);
         SA_LAUNCH_CHECK();
     }
+    // the tables were built on `st`; other streams may pick the plan up from the cache right away,
+    // so they must be complete before it is published (one-time cost per plan)
+    SA_CUDA(cudaStreamSynchronize(st));
     auto ins = g_plans.emplace(key, p);
     *plan_out = &ins.first->second;
     return SA_OK;
@@ -899,6 +902,7 @@ static int get_xinv(fe **out, const fe &omega, size_t n, cudaStream_t st) {
     fe *tab = nullptr;
     int rc = build_pow_table(&tab, winv_m, fe_mont_one(), (long long)(n / 2), st);
     if (rc != SA_OK) return rc;
+    SA_CUDA(cudaStreamSynchronize(st));  // complete before other streams can find it in the cache
     g_xinv[key] = tab;
     *out = tab;
     return SA_OK;
