@@ -18,6 +18,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
 
 
+def pytest_sessionstart(session):
+    """Make sure every native piece exists before tests import it (no-op when up to date): the
+    CUDA library and the marshalling extension are built in-tree and are not part of the git
+    history, so a fresh checkout has to compile them once (nvcc cross-compiles without a GPU)."""
+    try:
+        import __graft_entry__ as G
+        G.build_cuda()
+        G.build_marshal()
+        G.build_oracle()
+        G.build_emu()
+    except Exception as exc:  # let the individual tests report what is missing
+        print("conftest: native build step failed: %r" % (exc,))
+
+
 def load_golden(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)
