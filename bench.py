@@ -301,9 +301,18 @@ def run_ours(args):
         return
 
     # ---- CPU baseline on this box's host cores, bounded sample (a few seconds); N = 1 only
-    cpu_value = cpu_threads = None
+    cpu_value = cpu_threads = py_value = None
     if world == 1:
         cpu_value, cpu_threads, cpu_dt = cpu_arm(2, 1, BATCH)
+        # the reference is pure Python: time the literal Python restatement of ntt.py:3-18 (oracle.py
+        # py_ntt, ints instead of FieldElement objects) on one core at 2^12 as the same-run interpreter arm
+        import random
+        rng = random.Random(0)
+        pn = 1 << 12
+        pv = [rng.randrange(O.P) for _ in range(pn)]
+        t0 = time.perf_counter()
+        O.py_ntt(O.primitive_nth_root(pn), pv)
+        py_value = (pn // 2) * 12 / (time.perf_counter() - t0)
 
     # roofline of the dominant kernel, ntt_tile_kernel<10>: two launches per step (column pass, row pass);
     # each launch reads and writes the whole batch once: 32 * n * BATCH algorithmic bytes
@@ -336,6 +345,9 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP); reference "
                                    "pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
+        "cpu_python": {"value": py_value, "unit": UNIT, "cores": 1, "kind": "port",
+                       "sample": "oracle.py py_ntt at n = 2^12; the reference's own ntt measured 3.9e4-6.4e4 "
+                                 "butterflies/s at 2^10..2^20 on one Xeon core (BASELINE.md section 2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * 16,
                 "d2h_bytes_per_step": BATCH * N * 16, "api": "sa_ntt_host (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
