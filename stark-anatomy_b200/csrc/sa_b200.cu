@@ -663,13 +663,26 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
 // three internal streams so that the upload of chunk i+1, the kernels of chunk i and the download
 // of chunk i-1 overlap (PCIe is full duplex); with pinned host buffers the call is bound by the
 // slower copy direction instead of the sum of both.
-static cudaStream_t g_copy_streams[3];
-static cudaEvent_t g_copy_events[4];
+constexpr int HOST_STREAMS_MAX = 8;
+static cudaStream_t g_copy_streams[HOST_STREAMS_MAX];
+static cudaEvent_t g_copy_events[HOST_STREAMS_MAX + 1];
+static int g_host_streams = 3;            // SA_HOST_STREAMS
+static size_t g_host_chunk = 16u << 20;   // SA_HOST_CHUNK_MIB: bytes per pipelined chunk
 static int copy_streams_ready() {
     static bool ready = false;
     if (ready) return SA_OK;
-    for (int i = 0; i < 3; i++) SA_CUDA(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 4; i++) SA_CUDA(cudaEventCreateWithFlags(&g_copy_events[i], cudaEventDisableTiming));
+    if (const char *e = getenv("SA_HOST_STREAMS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= HOST_STREAMS_MAX) g_host_streams = v;
+    }
+    if (const char *e = getenv("SA_HOST_CHUNK_MIB")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 1024) g_host_chunk = (size_t)v << 20;
+    }
+    for (int i = 0; i < g_host_streams; i++)
+        SA_CUDA(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i <= g_host_streams; i++)
+        SA_CUDA(cudaEventCreateWithFlags(&g_copy_events[i], cudaEventDisableTiming));
     ready = true;
     return SA_OK;
 }
@@ -682,8 +695,9 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     const size_t bytes = one * batch;
     if (bytes == 0) return SA_OK;
     int rc;
-    // chunk = as many transforms as fit ~16 MiB (one 2^20 transform); small jobs stay on `st`
-    size_t per_chunk = one >= (size_t(16) << 20) ? 1 : (size_t(16) << 20) / one;
+    if ((rc = copy_streams_ready()) != SA_OK) return rc;
+    // chunk = as many transforms as fit g_host_chunk (default one 2^20 transform); small jobs stay on `st`
+    size_t per_chunk = one >= g_host_chunk ? 1 : g_host_chunk / one;
     if (per_chunk > batch) per_chunk = batch;
     const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
     if (nchunks < 2) {
@@ -695,26 +709,26 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
         SA_CUDA(cudaStreamSynchronize(st));
         return rc;
     }
-    if ((rc = copy_streams_ready()) != SA_OK) return rc;
-    // two device buffers per copy stream (the D2H of chunk c must not race the H2D of chunk c+3)
-    void *buf[3][2];
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 2; j++)
-            if ((rc = get_workspace(&buf[i][j], per_chunk * one, g_copy_streams[i], 1 + j)) != SA_OK) return rc;
-    SA_CUDA(cudaEventRecord(g_copy_events[3], st));
-    for (int i = 0; i < 3; i++) SA_CUDA(cudaStreamWaitEvent(g_copy_streams[i], g_copy_events[3], 0));
+    const int ns = g_host_streams;
+    void *buf[HOST_STREAMS_MAX];
+    for (int i = 0; i < ns; i++)
+        if ((rc = get_workspace(&buf[i], per_chunk * one, g_copy_streams[i], 1)) != SA_OK) return rc;
+    SA_CUDA(cudaEventRecord(g_copy_events[ns], st));
+    for (int i = 0; i < ns; i++) SA_CUDA(cudaStreamWaitEvent(g_copy_streams[i], g_copy_events[ns], 0));
     rc = SA_OK;
     for (size_t c = 0; c < nchunks && rc == SA_OK; c++) {
-        const int si = (int)(c % 3), bi = (int)((c / 3) % 2);
+        const int si = (int)(c % ns);
         cudaStream_t cs = g_copy_streams[si];
         const size_t first = c * per_chunk, cnt = (first + per_chunk <= batch) ? per_chunk : batch - first;
         const char *src = (const char *)in_host + first * one;
         char *dst = (char *)out_host + first * one;
-        SA_CUDA(cudaMemcpyAsync(buf[si][bi], src, cnt * one, cudaMemcpyHostToDevice, cs));
-        rc = sa_ntt(buf[si][bi], buf[si][bi], log_n, root, inverse, cnt, (void *)cs);
-        if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(dst, buf[si][bi], cnt * one, cudaMemcpyDeviceToHost, cs));
+        // within one stream the copies and kernels of successive chunks are ordered, so one device
+        // buffer per stream is enough; different streams overlap upload, kernels and download
+        SA_CUDA(cudaMemcpyAsync(buf[si], src, cnt * one, cudaMemcpyHostToDevice, cs));
+        rc = sa_ntt(buf[si], buf[si], log_n, root, inverse, cnt, (void *)cs);
+        if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(dst, buf[si], cnt * one, cudaMemcpyDeviceToHost, cs));
     }
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < ns; i++) {
         SA_CUDA(cudaEventRecord(g_copy_events[i], g_copy_streams[i]));
         SA_CUDA(cudaStreamWaitEvent(st, g_copy_events[i], 0));
     }
