@@ -47,6 +47,27 @@ def down(eng, vec):
 
 def test_field_selftest(eng):
     assert eng.lib.sa_selftest_field(1 << 20, 12345) == 0
+    assert eng.lib.sa_selftest_field(1 << 24, 987654321) == 0
+
+
+def test_ntt_random_campaign(eng):
+    """200 random (size, batch, direction, primitive root) combinations against the oracle"""
+    rng = random.Random(4242)
+    for it in range(200):
+        log_n = rng.randrange(1, 15)
+        n = 1 << log_n
+        batch = rng.choice([1, 1, 2, 3, 5, 8, 13])
+        inverse = rng.random() < 0.5
+        w = pow(O.primitive_nth_root(n), 2 * rng.randrange(n // 2 if n > 2 else 1) + 1, P)  # odd power: still primitive
+        x = rand_np(5000 + it, n * batch)
+        if it % 7 == 0:
+            x[rng.randrange(n * batch)] = O._fe(P - 1)
+            x[rng.randrange(n * batch)] = 0
+        got = down(eng, eng.ntt(up(eng, x), log_n, w, inverse=inverse, batch=batch))
+        for b in range(batch):
+            xb = x[b * n:(b + 1) * n]
+            want = O.intt_np(w, xb) if inverse else O.ntt_np(w, xb)
+            assert (got[b * n:(b + 1) * n] == want).all(), (it, log_n, batch, inverse)
 
 
 @pytest.mark.parametrize("log_n", list(range(1, 21)))
