@@ -24,6 +24,9 @@ struct MerkleArgs {
     long long width;     // number of bottom nodes of this launch
     int chunk;           // bottom nodes per CTA (power of two, <= MK_THREADS << ipt_log)
     int ipt_log;         // log2 of the bottom nodes one thread reduces privately (0..3)
+    int red_log;         // tree levels the CTA then reduces through shared memory (0..log2(chunk) - ipt_log);
+                         // the launch leaves width >> (ipt_log + red_log) digests for the next one
+    int coop_max;        // shared-memory levels of at most this many nodes are hashed four lanes per node
     int mode;            // 0: bottom digests already in tree; 1: leaves from `values`; 2: leaves from a fold
     const fe *values;    // mode 1: the codeword (width elements)
     const fe *prev;      // mode 2: the codeword being folded (2 * width elements)
@@ -34,9 +37,18 @@ struct MerkleArgs {
 };
 
 // launch shape for a level of `width` bottom nodes: small levels are latency bound (one node per
-// thread, as many CTAs as possible), big ones throughput bound (four leaves and their three
-// parents per thread, no barrier in between)
+// thread, as many CTAs as possible, each CTA reducing its chunk to one digest); big ones are
+// throughput bound: four leaves and their three parents per thread, barrier free, then only the three
+// shared-memory levels that still fill whole warps (128, 64, 32 nodes) - the 32 digests a CTA leaves
+// are picked up by the next launch, so no SM sits in a mostly idle dependency chain while thousands
+// of leaves wait (profiles/r01g_merkle_shapes.txt)
+SA_HD int merkle_log2(long long x) {
+    int l = 0;
+    while ((1ll << l) < x) l++;
+    return l;
+}
 SA_HD void merkle_shape(MerkleArgs &a) {
+    a.coop_max = MK_THREADS / 4;  // latency bound: a level of <= 64 nodes keeps all 256 lanes busy that way
     if (a.width <= MK_THREADS) {  // one CTA finishes the tree
         a.ipt_log = 0;
         a.chunk = (int)a.width;
@@ -46,11 +58,17 @@ SA_HD void merkle_shape(MerkleArgs &a) {
     } else if (a.width < (1 << 18)) {
         a.ipt_log = 1;
         a.chunk = MK_THREADS << 1;
-    } else {  // throughput bound: 4 bottom nodes + their 3 parents per thread, barrier free
+    } else {  // throughput bound
         a.ipt_log = 2;
         a.chunk = MK_THREADS << 2;
+        a.red_log = 3;
+        a.coop_max = 0;  // one thread per node issues fewer instructions per node
+        return;
     }
+    a.red_log = merkle_log2(a.chunk) - a.ipt_log;  // each CTA reduces its chunk to one digest
 }
+// width of the level a launch of shape `a` leaves behind
+SA_HD long long merkle_next_width(const MerkleArgs &a) { return a.width >> (a.ipt_log + a.red_log); }
 
 // digest of bottom node g of this launch: loads it (mode 0) or hashes the leaf (modes 1, 2) and
 // writes it to the tree (and next[] in mode 2)

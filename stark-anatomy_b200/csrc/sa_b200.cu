@@ -274,17 +274,18 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
     const long long blk = blockIdx.x;
     const int active = a.chunk >> a.ipt_log;  // threads with a private subtree
     uint64_t d[8];
+    if (tid < active) merkle_private(d, a, blk, tid);
+    if (a.red_log == 0) return;  // the next launch picks the subtree roots up from the tree
     if (tid < active) {
-        merkle_private(d, a, blk, tid);
 #pragma unroll
         for (int i = 0; i < 8; i++) sm[tid * 8 + i] = d[i];
     }
     __syncthreads();
     // index of thread 0's subtree root; the level above it starts at base >> 1, and so on
     long long base = (a.width + blk * a.chunk) >> a.ipt_log;
-    for (int wl = active / 2; wl >= 1; wl >>= 1) {
+    for (int wl = active / 2, lvl = 0; lvl < a.red_log; wl >>= 1, lvl++) {
         base >>= 1;
-        if (wl > MK_THREADS / 4) {  // plenty of nodes: one thread per node
+        if (wl > a.coop_max || wl > MK_THREADS / 4) {  // plenty of nodes: one thread per node
             const bool mine = tid < wl;
             if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
             __syncthreads();
@@ -836,14 +837,38 @@ int sa_interpolate(void *out, const void *domain, const void *values, size_t k, 
 }
 
 // ---- Merkle / FRI ----
+#ifdef SA_TUNE
+// SA_MK_SHAPE="minlog:ipt:chunklog:red:coopmax,..." overrides the launch shape of levels with width >= 2^minlog
+static void merkle_shape_env(MerkleArgs &a) {
+    const char *e = getenv("SA_MK_SHAPE");
+    if (!e) return;
+    int best = -1, w = merkle_log2(a.width);
+    while (*e) {
+        int ml, ipt, cl, red, coop, used = 0;
+        if (sscanf(e, "%d:%d:%d:%d:%d%n", &ml, &ipt, &cl, &red, &coop, &used) != 5) break;
+        if (ml <= w && ml > best && cl <= w) {
+            best = ml;
+            a.ipt_log = ipt;
+            a.chunk = 1 << cl;
+            a.red_log = red;
+            a.coop_max = coop;
+        }
+        e += used;
+        if (*e == ',') e++;
+    }
+}
+#endif
 static int merkle_reduce(MerkleArgs a, cudaStream_t st) {
     // first launch handles the bottom level in a.mode, later launches continue from digests
     while (true) {
         merkle_shape(a);
+#ifdef SA_TUNE
+        merkle_shape_env(a);
+#endif
         k_merkle_chunk<<<(unsigned)(a.width / a.chunk), MK_THREADS, 0, st>>>(a);
         SA_LAUNCH_CHECK();
-        if (a.width <= a.chunk) break;
-        a.width /= a.chunk;
+        if (merkle_next_width(a) <= 1) break;
+        a.width = merkle_next_width(a);
         a.mode = 0;
     }
     return SA_OK;

@@ -218,20 +218,34 @@ void emu_node_digest(uint8_t *out64, const uint8_t *left, const uint8_t *right) 
 
 // mirrors merkle_reduce / k_merkle_chunk (sa_b200.cu): private subtrees, then the shared-memory
 // reduction, heap-ordered tree
+static std::vector<int> g_mk_shape;  // (minlog, ipt_log, chunk_log, red_log, coop_max) rows; tests try other launch shapes
+static void emu_merkle_shape_override(MerkleArgs &a) {
+    int best = -1;
+    const int w = merkle_log2(a.width);
+    for (size_t i = 0; i + 4 < g_mk_shape.size(); i += 5)
+        if (g_mk_shape[i] <= w && g_mk_shape[i] > best && g_mk_shape[i + 2] <= w) {
+            best = g_mk_shape[i];
+            a.ipt_log = g_mk_shape[i + 1];
+            a.chunk = 1 << g_mk_shape[i + 2];
+            a.red_log = g_mk_shape[i + 3];
+            a.coop_max = g_mk_shape[i + 4];
+        }
+}
 static void emu_merkle_reduce(MerkleArgs a) {
     std::vector<uint64_t> sm((size_t)MK_THREADS * 8);
     while (true) {
         merkle_shape(a);
+        emu_merkle_shape_override(a);
         const long long blocks = a.width / a.chunk;
         const int active = a.chunk >> a.ipt_log;
         for (long long blk = 0; blk < blocks; blk++) {
             for (int tid = 0; tid < active; tid++) merkle_private(&sm[(size_t)tid * 8], a, blk, tid);
             long long base = (a.width + blk * a.chunk) >> a.ipt_log;
-            for (int wl = active / 2; wl >= 1; wl >>= 1) {
+            for (int wl = active / 2, lvl = 0; lvl < a.red_log; wl >>= 1, lvl++) {
                 base >>= 1;
                 std::vector<uint64_t> regs((size_t)wl * 8);
                 for (int tid = 0; tid < wl; tid++) {  // phase 1: read children, hash
-                    if (wl > MK_THREADS / 4)
+                    if (wl > a.coop_max)
                         merkle_node_digest(&regs[(size_t)tid * 8], &sm[(size_t)(2 * tid) * 8],
                                            &sm[(size_t)(2 * tid + 1) * 8]);
                     else  // the four-lanes-per-node schedule of the small levels
@@ -244,11 +258,12 @@ static void emu_merkle_reduce(MerkleArgs a) {
                     }
             }
         }
-        if (a.width <= a.chunk) break;
-        a.width /= a.chunk;
+        if (merkle_next_width(a) <= 1) break;
+        a.width = merkle_next_width(a);
         a.mode = 0;
     }
 }
+void emu_set_merkle_shape(const int *rows, int nrows) { g_mk_shape.assign(rows, rows + 5 * nrows); }
 int emu_merkle_tree(uint8_t *tree, const uint64_t *values, size_t n) {
     memset(tree, 0, 64);
     MerkleArgs a;

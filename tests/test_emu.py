@@ -141,3 +141,24 @@ def test_merkle_and_fri_round(E, logn):
         want = O.fri_fold_np(x, alpha, off, omega)
         assert (nxt == want).all()
         assert (ntree[1:] == O.merkle_tree_np(want)[1:]).all()
+
+
+@pytest.mark.parametrize("rows", [
+    [(10, 2, 10, 0, 64)],                    # barrier-free bottom launch, the rest by the default shape
+    [(8, 2, 10, 3, 0), (0, 0, 3, 1, 64)],    # partial in-CTA reduction; tiny launches of 8-node CTAs one level each
+    [(12, 3, 11, 2, 16), (6, 1, 6, 0, 0)],  # eight bottom nodes per thread; two per thread without shared phase
+])
+def test_merkle_other_launch_shapes(E, rows):
+    """the generalised launch shape (ipt_log, chunk, red_log) builds the same tree whatever the split"""
+    flat = (ctypes.c_int * (5 * len(rows)))(*[v for r in rows for v in r])
+    rng = random.Random(77)
+    try:
+        E.emu_set_merkle_shape(flat, len(rows))
+        for logn in (3, 6, 10, 13):
+            n = 1 << logn
+            x = O.to_np([rng.randrange(P) for _ in range(n)])
+            tree = np.zeros((2 * n, 64), dtype=np.uint8)
+            E.emu_merkle_tree(O._ptr(tree), O._ptr(x), ctypes.c_size_t(n))
+            assert (tree[1:] == O.merkle_tree_np(x)[1:]).all()
+    finally:
+        E.emu_set_merkle_shape(flat, 0)

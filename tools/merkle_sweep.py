@@ -14,6 +14,14 @@ eng = sa_engine.get_engine()
 lib, dev = eng.lib, eng.device
 st = torch.cuda.current_stream()
 sp = ctypes.c_void_p(st.cuda_stream)
+# parity spot check of whichever build was loaded (all launch shapes: 2^12 and 2^18 leaves)
+import numpy as np
+for chk in (12, 18):
+    xs = torch.randint(0, 1 << 62, (1 << chk, 2), dtype=torch.int64, device=dev)
+    xs[:, 1] &= (1 << 61) - 1
+    t = eng.merkle_tree(xs)
+    want = O.merkle_tree_np(xs.cpu().numpy().view(np.uint64))
+    assert (t.cpu().numpy()[1:] == want[1:]).all(), "merkle parity FAILED at 2^%d" % chk
 logs = [int(a) for a in sys.argv[1:]] or [1, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20]
 P = O.P
 for log_n in logs:
