@@ -34,6 +34,8 @@ struct MerkleArgs {
     const fe *xinv;      // mode 2: xinv[i] = omega^-i in Montgomery form, i < width
     fe s_m;              // mode 2: alpha * 2^-1 * offset^-1 in Montgomery form
     fe inv2_m;           // mode 2: 2^-1 in Montgomery form
+    uint64_t *root_out;  // last launch of a tree, optional: host-mapped landing pad, receives the root
+    unsigned long long root_seq;  // (8 words) and then this sequence number in word 8
 };
 
 // launch shape for a level of `width` bottom nodes: small levels are latency bound (one node per

@@ -268,6 +268,16 @@ __global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xin
 // Phase 1: every thread reduces its 2^ipt_log bottom nodes privately (no barrier); phase 2: the
 // per-thread digests are reduced through shared memory.  mode 2 is the fused FRI round:
 // fold -> leaf digest -> subtree, one pass over the codeword.
+// the host waits for the root of every FRI round before it can draw the next challenge: the last CTA
+// of a tree writes it straight into mapped host memory, followed (system-scope fence) by a sequence
+// number the host spins on - no copy engine, no stream synchronisation on the critical path
+__device__ __forceinline__ void merkle_publish_root(const MerkleArgs &a, const uint64_t *root) {
+    volatile uint64_t *out = a.root_out;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = root[i];
+    __threadfence_system();
+    out[8] = a.root_seq;
+}
 __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
     __shared__ uint64_t sm[MK_THREADS * 8];
     const int tid = threadIdx.x;
@@ -275,7 +285,10 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
     const int active = a.chunk >> a.ipt_log;  // threads with a private subtree
     uint64_t d[8];
     if (tid < active) merkle_private(d, a, blk, tid);
-    if (a.red_log == 0) return;  // the next launch picks the subtree roots up from the tree
+    if (a.red_log == 0) {  // the next launch picks the subtree roots up from the tree
+        if (a.root_out && tid == 0) merkle_publish_root(a, d);  // (a tree of one leaf)
+        return;
+    }
     if (tid < active) {
 #pragma unroll
         for (int i = 0; i < 8; i++) sm[tid * 8 + i] = d[i];
@@ -313,6 +326,7 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
         }
         __syncthreads();
     }
+    if (a.root_out && tid == 0) merkle_publish_root(a, sm);
 }
 
 __global__ void k_merkle_paths(uint64_t *out, const uint64_t *tree, long long n, int depth,
@@ -858,16 +872,19 @@ static void merkle_shape_env(MerkleArgs &a) {
     }
 }
 #endif
-static int merkle_reduce(MerkleArgs a, cudaStream_t st) {
+static int merkle_reduce(MerkleArgs a, cudaStream_t st, uint64_t *root_host = nullptr, unsigned long long seq = 0) {
     // first launch handles the bottom level in a.mode, later launches continue from digests
     while (true) {
         merkle_shape(a);
 #ifdef SA_TUNE
         merkle_shape_env(a);
 #endif
+        const bool last = merkle_next_width(a) <= 1;
+        a.root_out = last ? root_host : nullptr;
+        a.root_seq = seq;
         k_merkle_chunk<<<(unsigned)(a.width / a.chunk), MK_THREADS, 0, st>>>(a);
         SA_LAUNCH_CHECK();
-        if (merkle_next_width(a) <= 1) break;
+        if (last) break;
         a.width = merkle_next_width(a);
         a.mode = 0;
     }
@@ -990,13 +1007,45 @@ int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const ui
     return merkle_reduce(a, st);
 }
 
+// spin until the kernel has published root number `seq` (see merkle_publish_root); the stream is
+// polled now and then so that a failed launch turns into an error instead of a hang
+static int wait_for_root(uint64_t *root_host, unsigned long long seq, cudaStream_t st) {
+    volatile uint64_t *flag = root_host + 8;
+    for (unsigned spins = 1; *flag != seq; spins++) {
+        if ((spins & 0xfff) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) {
+                if (*flag == seq) break;
+                g_last_error = "sa_fri_commit: the stream drained without publishing the round root";
+                return SA_ECUDA;
+            }
+            if (q != cudaErrorNotReady) {
+                g_last_error = std::string("sa_fri_commit: ") + cudaGetErrorString(q);
+                return SA_ECUDA;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return SA_OK;
+}
+
 int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int rounds,
                   const uint64_t offset[2], const uint64_t omega[2], sa_fri_challenge_fn challenge, void *user,
                   void *stream) {
     if (!host_is_pow2(n) || rounds < 1 || (n >> (rounds - 1)) < 1) return SA_ESIZE;
     cudaStream_t st = (cudaStream_t)stream;
-    static uint8_t *root_pinned = nullptr;  // 64-byte landing pad for the per-round root
-    if (!root_pinned) SA_CUDA(cudaHostAlloc((void **)&root_pinned, 64, cudaHostAllocDefault));
+    // landing pad of the per-round root (8 words) + sequence number, written by the kernel itself
+    static thread_local uint64_t *root_pinned = nullptr;
+    static thread_local uint64_t *root_dev = nullptr;  // the same memory as the device addresses it
+    static thread_local unsigned long long root_seq = 0;
+    if (!root_pinned) {
+        SA_CUDA(cudaHostAlloc((void **)&root_pinned, 128, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(root_pinned, 0, 128);
+    }
+    SA_CUDA(cudaHostGetDevicePointer((void **)&root_dev, root_pinned, 0));  // per current device
     fe off = fe_from_limbs(offset), om = fe_from_limbs(omega);
     // host-side scalars of the fold: 2^-1 once, offset^-1 once and then squared along with offset
     // (a Fermat inversion on the host costs ~10 us; per round that was a fifth of the round trip)
@@ -1018,15 +1067,14 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
             a.width = (long long)len;
             a.mode = 1;
             a.values = cur;
-            if ((rc = merkle_reduce(a, st)) != SA_OK) return rc;
+            if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
         }
         const double t_launched = now();
-        SA_CUDA(cudaMemcpyAsync(root_pinned, tree + 64, 64, cudaMemcpyDeviceToHost, st));
-        SA_CUDA(cudaStreamSynchronize(st));
+        if ((rc = wait_for_root(root_pinned, root_seq, st)) != SA_OK) return rc;
         const double t_synced = now();
         uint64_t alpha[2] = {0, 0};
         const int want = r != rounds - 1;
-        if (challenge(user, r, root_pinned, alpha, want) != 0) return SA_ECALLBACK;
+        if (challenge(user, r, (const uint8_t *)root_pinned, alpha, want) != 0) return SA_ECALLBACK;
         if (trace) {
             const double t_cb = now();
             fprintf(stderr, "sa_fri_commit round %2d len %8zu: launch %.1f us, wait %.1f us, callback %.1f us\n", r, len,
@@ -1048,7 +1096,7 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
         a.xinv = xinv;
         a.inv2_m = inv2_m;
         a.s_m = fe_montmul(fe_montmul(fe_to_mont(fe_from_limbs(alpha)), inv2_m), oinv_m);  // alpha / (2 offset)
-        if ((rc = merkle_reduce(a, st)) != SA_OK) return rc;
+        if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
         cur = layer_out;
         layer_out += len / 2;
         tree = next_tree;
