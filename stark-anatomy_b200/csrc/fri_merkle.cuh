@@ -34,6 +34,8 @@ struct MerkleArgs {
     const fe *xinv;      // mode 2: xinv[i] = omega^-i in Montgomery form, i < width
     fe s_m;              // mode 2: alpha * 2^-1 * offset^-1 in Montgomery form
     fe inv2_m;           // mode 2: 2^-1 in Montgomery form
+    unsigned int *ticket;  // optional: CTA arrival counter (zero between launches); the CTA that arrives last
+                         // also reduces the gridDim.x (<= MK_THREADS) subtree roots, saving a launch
     uint64_t *root_out;  // last launch of a tree, optional: host-mapped landing pad, receives the root
     unsigned long long root_seq;  // (8 words) and then this sequence number in word 8
 };

@@ -296,35 +296,61 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
     __syncthreads();
     // index of thread 0's subtree root; the level above it starts at base >> 1, and so on
     long long base = (a.width + blk * a.chunk) >> a.ipt_log;
-    for (int wl = active / 2, lvl = 0; lvl < a.red_log; wl >>= 1, lvl++) {
-        base >>= 1;
-        if (wl > a.coop_max || wl > MK_THREADS / 4) {  // plenty of nodes: one thread per node
-            const bool mine = tid < wl;
-            if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
-            __syncthreads();
-            if (mine) {
-                uint64_t *node = a.tree + (base + tid) * 8;
+    int wl = active / 2, levels = a.red_log, coop_max = a.coop_max;
+    for (int pass = 0;; pass++) {
+        for (int lvl = 0; lvl < levels; wl >>= 1, lvl++) {
+            base >>= 1;
+            if (wl > coop_max || wl > MK_THREADS / 4) {  // plenty of nodes: one thread per node
+                const bool mine = tid < wl;
+                if (mine) merkle_node_digest(d, sm + (2 * tid) * 8, sm + (2 * tid + 1) * 8);
+                __syncthreads();
+                if (mine) {
+                    uint64_t *node = a.tree + (base + tid) * 8;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    sm[tid * 8 + i] = d[i];
-                    node[i] = d[i];
+                    for (int i = 0; i < 8; i++) {
+                        sm[tid * 8 + i] = d[i];
+                        node[i] = d[i];
+                    }
+                }
+            } else {  // few nodes, the level is a dependency chain: four lanes per node (hash.cuh)
+                const int q = tid >> 2, j = tid & 3;
+                const bool warp_on = (tid >> 5) < ((4 * wl + 31) >> 5);  // whole warps only (shuffles)
+                uint64_t lo = 0, hi = 0;
+                if (warp_on) blake2b_coop4_node(lo, hi, sm + (2 * (q < wl ? q : 0)) * 8, j);
+                __syncthreads();
+                if (warp_on && q < wl) {
+                    uint64_t *node = a.tree + (base + q) * 8;
+                    sm[q * 8 + j] = lo;
+                    sm[q * 8 + 4 + j] = hi;
+                    node[j] = lo;
+                    node[4 + j] = hi;
                 }
             }
-        } else {  // few nodes, the level is a dependency chain: four lanes per node (hash.cuh)
-            const int q = tid >> 2, j = tid & 3;
-            const bool warp_on = (tid >> 5) < ((4 * wl + 31) >> 5);  // whole warps only (shuffles)
-            uint64_t lo = 0, hi = 0;
-            if (warp_on) blake2b_coop4_node(lo, hi, sm + (2 * (q < wl ? q : 0)) * 8, j);
             __syncthreads();
-            if (warp_on && q < wl) {
-                uint64_t *node = a.tree + (base + q) * 8;
-                sm[q * 8 + j] = lo;
-                sm[q * 8 + 4 + j] = hi;
-                node[j] = lo;
-                node[4 + j] = hi;
-            }
+        }
+        if (pass == 1 || a.ticket == nullptr) break;
+        // Every CTA has reduced its chunk to one digest (heap node gridDim.x + blk).  The CTA that
+        // arrives last reduces those gridDim.x digests as well instead of leaving them to one more
+        // launch (each thread fences its own stores, the barrier orders them before the ticket).
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!s_last) return;
+        const int g = (int)gridDim.x;
+        if (tid == 0) *a.ticket = 0;  // as the next launch on this stream expects it
+        __threadfence();
+        if (tid < g) {
+            const uint64_t *node = a.tree + (size_t)(g + tid) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sm[tid * 8 + i] = __ldcg(node + i);  // written by other SMs: not via L1
         }
         __syncthreads();
+        base = g;
+        wl = g / 2;
+        levels = 31 - __clz(g);
+        coop_max = MK_THREADS / 4;  // this part is a dependency chain whatever the shape below was
     }
     if (a.root_out && tid == 0) merkle_publish_root(a, sm);
 }
@@ -872,14 +898,36 @@ static void merkle_shape_env(MerkleArgs &a) {
     }
 }
 #endif
+// arrival counters of k_merkle_chunk's fused top, one per (device, stream): zero whenever no launch
+// of that stream is in flight (the last CTA resets it)
+static std::map<std::pair<int, cudaStream_t>, unsigned int *> g_tickets;
+static unsigned int *get_ticket(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    auto &slot = g_tickets[std::make_pair(dev, st)];
+    if (!slot) {
+        if (cudaMalloc((void **)&slot, 256) != cudaSuccess || cudaMemset(slot, 0, 256) != cudaSuccess) {
+            slot = nullptr;
+            cudaGetLastError();
+        }
+    }
+    return slot;  // nullptr: fall back to one more launch
+}
 static int merkle_reduce(MerkleArgs a, cudaStream_t st, uint64_t *root_host = nullptr, unsigned long long seq = 0) {
+    static const bool no_fuse = getenv("SA_MK_NO_FUSED_TOP") != nullptr;  // A/B switch for measurements
+    unsigned int *ticket = no_fuse ? nullptr : get_ticket(st);
     // first launch handles the bottom level in a.mode, later launches continue from digests
     while (true) {
         merkle_shape(a);
 #ifdef SA_TUNE
         merkle_shape_env(a);
 #endif
-        const bool last = merkle_next_width(a) <= 1;
+        // the launch that leaves at most MK_THREADS single-digest CTAs also reduces those (ticket)
+        const long long left = merkle_next_width(a), grid = a.width / a.chunk;
+        const bool fuse_top = left > 1 && left <= MK_THREADS && left == grid && ticket != nullptr;
+        const bool last = left <= 1 || fuse_top;
+        a.ticket = fuse_top ? ticket : nullptr;
         a.root_out = last ? root_host : nullptr;
         a.root_seq = seq;
         k_merkle_chunk<<<(unsigned)(a.width / a.chunk), MK_THREADS, 0, st>>>(a);

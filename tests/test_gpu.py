@@ -288,6 +288,52 @@ def test_fri_round_and_fold(eng, log_n):
     assert (tree.cpu().numpy()[1:] == O.merkle_tree_np(want)[1:]).all()
 
 
+def test_merkle_and_fri_commit_two_streams_and_threads(eng):
+    """Merkle trees and whole FRI commits from two host threads on two streams at once: the fused-top
+    arrival counter is per stream and the mapped root landing pad per thread, so neither may leak
+    into the other's results"""
+    import threading
+    import torch
+    log_n = 13
+    n = 1 << log_n
+    omega, off = O.primitive_nth_root(n), O.GENERATOR
+    xs = [rand_np(700 + i, n) for i in range(2)]
+    alphas = [[random.Random(710 + i).randrange(P) for _ in range(8)] for i in range(2)]
+    got = [{"roots": [], "trees": []}, {"roots": [], "trees": []}]
+    errs = []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                v = up(eng, xs[i])
+                for rep in range(10):
+                    roots = []
+                    eng.fri_commit(v, 8, off, omega, lambda r, root, want: (roots.append(root), alphas[i][r])[1])
+                    got[i]["roots"].append(roots)
+                    got[i]["trees"].append(eng.merkle_tree(v).cpu().numpy())
+            st.synchronize()
+        except BaseException as exc:  # surfaces in the main thread
+            errs.append(exc)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        cw, o, w, want_roots = xs[i], off, omega, []
+        for r in range(8):
+            want_roots.append(O.merkle_tree_np(cw)[1].tobytes())
+            if r < 7:
+                cw = O.fri_fold_np(cw, alphas[i][r], o, w)
+                o, w = o * o % P, w * w % P
+        want_tree = O.merkle_tree_np(xs[i])
+        for rep in range(10):
+            assert got[i]["roots"][rep] == want_roots
+            assert (got[i]["trees"][rep][1:] == want_tree[1:]).all()
+
+
 # ---- the drop-in modules on the real engine, against the reference's golden outputs -------
 def test_dropin_ntt_vectors(eng):
     C.case_ntt_vectors()
