@@ -172,6 +172,8 @@ SA_HD fe fe_montmul_portable(const fe &a, const fe &b) {
 // ---- sm_100a versions: explicit carry chains.  ptxas fuses each
 // mad.lo.cc/madc.hi.cc pair into one IMAD.WIDE.U32(.X) with a predicate carry,
 // so the 4x4 product is 16 wide multiply-adds and the reduction 5 more.
+// SASS per operation (tools/sass_mix.py): montmul 21 IMAD.WIDE + ~13 IMAD + ~24 ALU, add 13 ALU,
+// sub 7 ALU + 3 IMAD.
 __device__ __forceinline__ fe fe_cond_sub_p(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t top) {
     uint32_t d0, d1, d2, d3, br;
     asm("sub.cc.u32 %0, %5, 1;\n\t"
@@ -184,6 +186,37 @@ __device__ __forceinline__ fe fe_cond_sub_p(uint32_t r0, uint32_t r1, uint32_t r
     bool use = (top != 0) | (br == 0);
     return fe_make(use ? d0 : r0, use ? d1 : r1, use ? d2 : r2, use ? d3 : r3);
 }
+// (d3..d0) + p when m is all-ones, unchanged when m is zero (m = the borrow word of a subtraction that
+// went negative).  The two mask words (1 and P3, or zeros) are either ANDs (ALU pipe) or products of the
+// all-ones word (FMA pipe).  SA_FIELD_MASK says which are ANDs: bit 0 = montmul's w, bit 1 = montmul's
+// add-back, bit 2 = fe_sub's add-back.  Measured on the 16 x 2^20 NTT step (profiles/r01g_field_v2.txt):
+// 1 -> 0.737 ms, 0 -> 0.741, 4 -> 0.748, 7 -> 0.758.
+#ifndef SA_FIELD_MASK
+#define SA_FIELD_MASK 1
+#endif
+template <bool ALU_MASKS>
+__device__ __forceinline__ fe fe_cond_add_p(uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t m) {
+    uint32_t p0, p3;
+    if (ALU_MASKS) {
+        p0 = m & 1u;
+        p3 = m & 0xCB800000u;
+    } else {
+        asm("mul.lo.u32 %0, %2, %2;\n\t"           // (-1)^2 = 1
+            "mul.lo.u32 %1, %2, 0x34800000;"        // (-1) * (-P3) = P3
+            : "=r"(p0), "=r"(p3) : "r"(m));
+    }
+    uint32_t r0, r1, r2, r3;
+    asm("add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, 0;\n\t"
+        "addc.cc.u32 %2, %6, 0;\n\t"
+        "addc.u32 %3, %7, %9;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(p0), "r"(p3));
+    return fe_make(r0, r1, r2, r3);
+}
+// a five-limb sum, the trial subtraction of p and a predicated select: 13 ALU instructions (the
+// a - (p - b) form with the masked add-back needs 14 plus two multiplies, and ptxas does not fuse
+// a + b + (2^128 - p) into three-input IADD3 chains)
 __device__ __forceinline__ fe fe_add(const fe &a, const fe &b) {
     uint32_t s0, s1, s2, s3, c;
     asm("add.cc.u32 %0, %5, %9;\n\t"
@@ -206,15 +239,7 @@ __device__ __forceinline__ fe fe_sub(const fe &a, const fe &b) {
         : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(m)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]),
           "r"(b.v[3]));
-    uint32_t p0 = m & 1u, p3 = m & 0xCB800000u;  // m = all-ones on borrow: add p back
-    uint32_t r0, r1, r2, r3;
-    asm("add.cc.u32 %0, %4, %8;\n\t"
-        "addc.cc.u32 %1, %5, 0;\n\t"
-        "addc.cc.u32 %2, %6, 0;\n\t"
-        "addc.u32 %3, %7, %9;"
-        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-        : "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(p0), "r"(p3));
-    return fe_make(r0, r1, r2, r3);
+    return fe_cond_add_p<((SA_FIELD_MASK) >> 2) & 1>(d0, d1, d2, d3, m);
 }
 __device__ __forceinline__ fe fe_montmul(const fe &a, const fe &b) {
     uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3];
@@ -269,18 +294,22 @@ __device__ __forceinline__ fe fe_montmul(const fe &a, const fe &b) {
           "=&r"(o0), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4), "=&r"(o5), "=&r"(o6)
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3));
     (void)o0; (void)o1; (void)o2; (void)o3; (void)o4; (void)o5; (void)o6;
-    // m = ((t0*P3 mod 2^32) << 96) - t_lo; borrow-out = carry of t_lo + m
+    // Reduction with p^-1 = 1 - P3*2^96 (mod 2^128) instead of -p^-1: m = t_lo * p^-1 mod 2^128 is t_lo
+    // with (t0*P3 mod 2^32) taken off its top word, and since t_lo - m and m*P3*2^96 cancel below bit
+    // 128,  t*2^-128 = t_hi - ((m*P3) >> 32) - w  (w = the borrow of that top word), in (-p, p): one
+    // masked add of p.  Half the ALU instructions of the m = -t_lo form (no 128-bit negation, no
+    // five-way select); the 0/1 words come from multiplies so that they issue on the FMA pipe.
     uint32_t x = e0 * P3;
-    uint32_t m0, m1, m2, m3, cam;
-    asm("sub.cc.u32 %0, 0, %5;\n\t"
-        "subc.cc.u32 %1, 0, %6;\n\t"
-        "subc.cc.u32 %2, 0, %7;\n\t"
-        "subc.cc.u32 %3, %9, %8;\n\t"
-        "subc.u32 %4, 0, 0;"
-        : "=r"(m0), "=r"(m1), "=r"(m2), "=r"(m3), "=r"(cam)
-        : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(x));
-    uint32_t k = (cam & 1u) + (x != 0u);
-    // (u1..u4) = (m * P3) >> 32, with k folded into the lowest word
+    uint32_t m3, nw;
+    asm("sub.cc.u32 %0, %2, %3;\n\t"
+        "subc.u32 %1, 0, 0;"
+        : "=r"(m3), "=r"(nw)
+        : "r"(e3), "r"(x));
+    uint32_t w;
+    if ((SA_FIELD_MASK) & 1)
+        w = nw & 1u;
+    else
+        asm("mul.lo.u32 %0, %1, %1;" : "=r"(w) : "r"(nw));  // nw is 0 or -1
     uint32_t u1, u2, u3, u4;
     asm("mad.hi.u32 %0, %4, 0xCB800000, %8;\n\t"
         "mad.lo.cc.u32 %0, %5, 0xCB800000, %0;\n\t"
@@ -290,16 +319,16 @@ __device__ __forceinline__ fe fe_montmul(const fe &a, const fe &b) {
         "mad.lo.cc.u32 %2, %7, 0xCB800000, %2;\n\t"
         "madc.hi.u32 %3, %7, 0xCB800000, 0;"
         : "=&r"(u1), "=&r"(u2), "=&r"(u3), "=&r"(u4)
-        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(k));
+        : "r"(e0), "r"(e1), "r"(e2), "r"(m3), "r"(w));
     uint32_t r0, r1, r2, r3, top;
-    asm("add.cc.u32 %0, %5, %9;\n\t"
-        "addc.cc.u32 %1, %6, %10;\n\t"
-        "addc.cc.u32 %2, %7, %11;\n\t"
-        "addc.cc.u32 %3, %8, %12;\n\t"
-        "addc.u32 %4, 0, 0;"
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;"
         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(top)
         : "r"(e4), "r"(e5), "r"(e6), "r"(e7), "r"(u1), "r"(u2), "r"(u3), "r"(u4));
-    return fe_cond_sub_p(r0, r1, r2, r3, top);
+    return fe_cond_add_p<((SA_FIELD_MASK) >> 1) & 1>(r0, r1, r2, r3, top);
 }
 #else
 SA_HD fe fe_add(const fe &a, const fe &b) { return fe_add_portable(a, b); }

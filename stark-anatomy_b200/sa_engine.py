@@ -14,7 +14,8 @@ import os
 
 P = 1 + 407 * (1 << 119)
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsa_b200.so")
+# SA_B200_LIB: another build of the same C ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("SA_B200_LIB") or os.path.join(_HERE, "libsa_b200.so")
 
 # include/sa_b200.h error codes -> the reference's assertion messages
 SA_ERRORS = {
