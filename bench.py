@@ -335,8 +335,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ntt_tile_kernel<10>", "launches_per_step": launches_per_step,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
-                     "note": "bound by the integer pipes, not HBM: ~900 int instructions per element put the "
-                             "floor at ~31 us per 2^20 transform = frac 0.33 (DESIGN.md 3.2, profiles/r01_notes.md)"},
+                     "note": "bound by the integer pipes, not HBM: 21 IMAD.WIDE per field product (4 fmaheavy cycles each) put "
+                             "the floor at ~30 us per 2^20 transform = frac 0.33 (DESIGN.md 3.2, profiles/r01_notes.md)"},
         "int_roofline": {"bound": "integer pipes (IMAD.WIDE / IADD3)", "achieved": value / world,
                          "peak": int_peak, "unit": "butterflies/s per GPU",
                          "frac": (value / world / int_peak) if int_peak else None,
