@@ -700,15 +700,18 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     return rc;
 }
 
-// Host entry: H2D, transforms, D2H.  Batches are cut into per-transform chunks that rotate over
-// three internal streams so that the upload of chunk i+1, the kernels of chunk i and the download
+// Host entry: H2D, transforms, D2H.  Batches are cut into chunks of a few transforms that rotate over
+// a few internal streams so that the upload of chunk i+1, the kernels of chunk i and the download
 // of chunk i-1 overlap (PCIe is full duplex); with pinned host buffers the call is bound by the
 // slower copy direction instead of the sum of both.
 constexpr int HOST_STREAMS_MAX = 8;
 static cudaStream_t g_copy_streams[HOST_STREAMS_MAX];
 static cudaEvent_t g_copy_events[HOST_STREAMS_MAX + 1];
-static int g_host_streams = 3;            // SA_HOST_STREAMS
-static size_t g_host_chunk = 16u << 20;   // SA_HOST_CHUNK_MIB: bytes per pipelined chunk
+static int g_host_streams = 4;            // SA_HOST_STREAMS
+static size_t g_host_chunk = 32u << 20;   // SA_HOST_CHUNK_MIB: bytes per pipelined chunk
+static int g_host_ramp = 1;               // SA_HOST_RAMP: first/last chunks start at chunk >> ramp
+// (measured, profiles/r01g_e2e_pipeline_sweep.txt: 4 streams x 32 MiB with a one-step ramp 6.35 ms per
+//  16 x 2^20 call, 3 x 16 MiB flat 6.48-6.58 ms; the link does 49.6 GB/s each way on monolithic copies)
 static int copy_streams_ready() {
     static bool ready = false;
     if (ready) return SA_OK;
@@ -719,6 +722,10 @@ static int copy_streams_ready() {
     if (const char *e = getenv("SA_HOST_CHUNK_MIB")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 1024) g_host_chunk = (size_t)v << 20;
+    }
+    if (const char *e = getenv("SA_HOST_RAMP")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 6) g_host_ramp = v;
     }
     for (int i = 0; i < g_host_streams; i++)
         SA_CUDA(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
@@ -737,7 +744,7 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     if (bytes == 0) return SA_OK;
     int rc;
     if ((rc = copy_streams_ready()) != SA_OK) return rc;
-    // chunk = as many transforms as fit g_host_chunk (default one 2^20 transform); small jobs stay on `st`
+    // chunk = as many transforms as fit g_host_chunk (default two 2^20 transforms); small jobs stay on `st`
     size_t per_chunk = one >= g_host_chunk ? 1 : g_host_chunk / one;
     if (per_chunk > batch) per_chunk = batch;
     const size_t nchunks = (batch + per_chunk - 1) / per_chunk;
@@ -751,18 +758,39 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
         return rc;
     }
     const int ns = g_host_streams;
+    // chunk sizes (in transforms): ramp up from a small first chunk and down to a small last one, so
+    // that the stretch where only one copy direction is busy (before the first kernel can start, after
+    // the last one has finished) is short while the bulk moves in few large copies
+    std::vector<size_t> counts;
+    {
+        std::vector<size_t> head;
+        if (g_host_ramp)
+            for (size_t c = per_chunk >> g_host_ramp; c < per_chunk; c <<= 1) head.push_back(c ? c : 1);
+        size_t ramp = 0;
+        for (size_t c : head) ramp += c;
+        if (2 * ramp >= batch) head.clear(), ramp = 0;
+        counts = head;
+        for (size_t left = batch - 2 * ramp; left > 0;) {
+            const size_t c = left < per_chunk ? left : per_chunk;
+            counts.push_back(c);
+            left -= c;
+        }
+        counts.insert(counts.end(), head.rbegin(), head.rend());
+    }
     void *buf[HOST_STREAMS_MAX];
     for (int i = 0; i < ns; i++)
         if ((rc = get_workspace(&buf[i], per_chunk * one, g_copy_streams[i], 1)) != SA_OK) return rc;
     SA_CUDA(cudaEventRecord(g_copy_events[ns], st));
     for (int i = 0; i < ns; i++) SA_CUDA(cudaStreamWaitEvent(g_copy_streams[i], g_copy_events[ns], 0));
     rc = SA_OK;
-    for (size_t c = 0; c < nchunks && rc == SA_OK; c++) {
+    size_t first = 0;
+    for (size_t c = 0; c < counts.size() && rc == SA_OK; c++) {
         const int si = (int)(c % ns);
         cudaStream_t cs = g_copy_streams[si];
-        const size_t first = c * per_chunk, cnt = (first + per_chunk <= batch) ? per_chunk : batch - first;
+        const size_t cnt = counts[c];
         const char *src = (const char *)in_host + first * one;
         char *dst = (char *)out_host + first * one;
+        first += cnt;
         // within one stream the copies and kernels of successive chunks are ordered, so one device
         // buffer per stream is enough; different streams overlap upload, kernels and download
         SA_CUDA(cudaMemcpyAsync(buf[si], src, cnt * one, cudaMemcpyHostToDevice, cs));
