@@ -71,6 +71,9 @@ static PyObject *sa_unpack_ints(PyObject *, PyObject *arg) {
     if (PyObject_GetBuffer(arg, &buf, PyBUF_SIMPLE) < 0) return nullptr;
     const Py_ssize_t n = buf.len / 16;
     PyObject *out = PyList_New(n);
+    // a million new instances would trigger the cyclic collector again and again, and every pass walks
+    // all of them (40 % of the call at 2^20): pause it while the list is filled
+    const int gc_was_on = PyGC_Disable();
     if (out) {
         const unsigned char *src = (const unsigned char *)buf.buf;
         for (Py_ssize_t i = 0; i < n; i++) {
@@ -99,6 +102,9 @@ static PyObject *sa_unpack(PyObject *, PyObject *args) {
     if (PyObject_GetBuffer(bufobj, &buf, PyBUF_SIMPLE) < 0) return nullptr;
     const Py_ssize_t n = buf.len / 16;
     PyObject *out = PyList_New(n);
+    // a million new instances would trigger the cyclic collector again and again, and every pass walks
+    // all of them (40 % of the call at 2^20): pause it while the list is filled
+    const int gc_was_on = PyGC_Disable();
     if (out) {
         const unsigned char *src = (const unsigned char *)buf.buf;
         for (Py_ssize_t i = 0; i < n; i++) {
@@ -114,6 +120,7 @@ static PyObject *sa_unpack(PyObject *, PyObject *args) {
             PyList_SET_ITEM(out, i, obj);
         }
     }
+    if (gc_was_on) PyGC_Enable();
     PyBuffer_Release(&buf);
     return out;
 }
