@@ -145,6 +145,26 @@ def test_ntt_in_place_and_host_entry(eng):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("log_n,batch", [(16, 70), (18, 9), (12, 3)])
+def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
+    """sa_ntt_host cuts a batch into ramped chunks over several copy streams (32 MiB chunks, first and
+    last halved): ragged batch sizes, chunk boundaries and the single-chunk path against the oracle"""
+    import torch
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    x = rand_np(1200 + log_n, n * batch)
+    want = O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2)
+    hx = torch.from_numpy(x.view(np.int64)).pin_memory()
+    hy = torch.empty_like(hx).pin_memory()
+    for inverse in (0, 1):
+        src = hx if not inverse else hy
+        rc = eng.lib.sa_ntt_host(hy.data_ptr(), src.data_ptr(), log_n, sa_engine._limbs(w), inverse, batch, eng._stream())
+        assert rc == 0
+        if not inverse:
+            assert (hy.numpy().view(np.uint64) == want).all()
+    assert (hy.numpy().view(np.uint64) == x).all()  # in-place inverse through the same pipeline
+
+
 def test_ntt_two_streams_and_threads(eng):
     """independent work on two CUDA streams from two host threads (per-stream workspaces, shared
     plan cache behind a mutex): results equal the oracle's"""
