@@ -129,3 +129,35 @@ print(hashlib.sha256(proof).hexdigest(), len(proof), ok, len(sa_engine.get_engin
     env = dict(os.environ, SA_B200_ACCEL_POLYMUL="1")
     out2 = subprocess.check_output([sys.executable, "-c", code], text=True, env=env).split()
     assert out2[:3] == out[:3] and int(out2[3]) > int(out[3])
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+@pytest.mark.parametrize("ref_test", ["test_ntt.py", "test_fri.py", "test_merkle.py"])
+def test_reference_own_tests_pass_against_the_dropin(ref_test):
+    """The reference's OWN test files (code/test_ntt.py, test_fri.py, test_merkle.py), unmodified,
+    collected from the read-only checkout with the drop-in directory ahead of code/ on sys.path:
+    their `from ntt import *` / `from fri import *` bind to stark-anatomy_b200/ntt.py and fri.py
+    (engine = the oracle-backed double, as everywhere in this file)."""
+    code = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path[:0] = [%(pkg)r, %(ref)r, %(oracle)r, %(tests)r]
+import sa_engine
+from fake_engine import OracleEngine
+sa_engine.set_engine(OracleEngine())
+import ntt, fri
+assert ntt.__file__.startswith(%(pkg)r) and fri.__file__.startswith(%(pkg)r)
+import pytest
+rc = pytest.main([%(target)r, "-q", "-x", "-k", "not colinearity", "-p", "no:cacheprovider",
+                  "--rootdir", %(ref)r, "-c", "/dev/null", "--import-mode=importlib"])
+eng = sa_engine.get_engine()
+print("RC", int(rc), "ENGINE_CALLS", len(eng.calls))
+''' % {"pkg": os.path.join(ROOT, "stark-anatomy_b200"), "ref": REFERENCE,
+       "oracle": os.path.join(ROOT, "oracle"), "tests": os.path.join(ROOT, "tests"),
+       "target": os.path.join(REFERENCE, ref_test)}
+    out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=900,
+                         cwd=os.path.join(ROOT, "tests"))
+    tail = out.stdout.strip().splitlines()[-1].split() if out.stdout.strip() else []
+    assert tail[:2] == ["RC", "0"], out.stdout[-2000:] + out.stderr[-2000:]
+    if ref_test != "test_merkle.py":  # (test_merkle.py hashes raw byte strings: stays on the host class)
+        assert int(tail[3]) > 0, "the reference test did not reach the engine"
