@@ -161,3 +161,32 @@ print("RC", int(rc), "ENGINE_CALLS", len(eng.calls))
     assert tail[:2] == ["RC", "0"], out.stdout[-2000:] + out.stderr[-2000:]
     if ref_test != "test_merkle.py":  # (test_merkle.py hashes raw byte strings: stays on the host class)
         assert int(tail[3]) > 0, "the reference test did not reach the engine"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_unmodified_fast_rpsss_sign_and_verify():
+    """BASELINE config 5's functional check: code/fast_rpsss.py and code/fast_stark.py, unmodified, on top
+    of the drop-in (with the opt-in device Polynomial.__mul__): keygen -> sign -> verify is True, and a
+    signature does not verify for another document.  (Reference alone: sign 29 s, verify 206 s.)"""
+    code = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path[:0] = [%(pkg)r, %(ref)r, %(oracle)r, %(tests)r]
+import sa_engine
+from fake_engine import OracleEngine
+sa_engine.set_engine(OracleEngine())
+import fast_rpsss, fast_stark, fri
+assert fast_rpsss.__file__.startswith(%(ref)r) and fast_stark.__file__.startswith(%(ref)r)
+assert fast_stark.Fri is fri.Fri and fri.__file__.startswith(%(pkg)r)
+r = fast_rpsss.FastRPSSS()
+sk, pk = r.keygen()
+sig = r.sign(sk, b"Hello, World!")
+print("RESULT", r.verify(pk, b"Hello, World!", sig), r.verify(pk, b"Byebye.", sig), len(sa_engine.get_engine().calls))
+''' % {"pkg": os.path.join(ROOT, "stark-anatomy_b200"), "ref": REFERENCE,
+       "oracle": os.path.join(ROOT, "oracle"), "tests": os.path.join(ROOT, "tests")}
+    env = dict(os.environ, SA_B200_ACCEL_POLYMUL="1")
+    out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=900, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, out.stdout[-2000:] + out.stderr[-2000:]
+    _, good, bad, calls = line[0].split()
+    assert good == "True" and bad == "False" and int(calls) > 50
