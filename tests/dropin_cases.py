@@ -99,6 +99,31 @@ def case_poly():
         assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_interpolate"
 
 
+def case_poly_split_recursion():
+    """domains larger than one device call handles (sa_engine.MAX_DIRECT_POINTS) go through the
+    reference's own halving recursion (ntt.py:76-80, :113-130) on top of the device pieces: force that
+    path with a tiny limit and replay the golden zerofier / interpolate cases through it"""
+    import sa_engine
+    eng = sa_engine.get_engine()
+    g = load_golden("poly.json")
+    saved = eng.MAX_DIRECT_POINTS
+    eng.MAX_DIRECT_POINTS = 3
+    try:
+        for c in g["zerofier"]:
+            got = N.fast_zerofier(T.elems(c["domain"]), T.fe(c["root"]), c["order"])
+            assert vals(got.coefficients) == [int(v) for v in c["out"]], "fast_zerofier (split)"
+        for c in g["interpolate"]:
+            got = N.fast_interpolate(T.elems(c["domain"]), T.elems(c["values"]), T.fe(c["root"]), c["order"])
+            want = [int(v) for v in c["out"]]
+            have = vals(got.coefficients)
+            # the recursion's schoolbook combination may carry trailing zeros the direct kernel does not
+            while len(have) > len(want) and have[-1] == 0:
+                have.pop()
+            assert have == want, "fast_interpolate (split)"
+    finally:
+        eng.MAX_DIRECT_POINTS = saved
+
+
 def case_poly_asserts():
     w = T.field.primitive_nth_root(64)
     a, b = T.poly(range(1, 20)), T.poly(range(3, 12))

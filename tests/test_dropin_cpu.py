@@ -44,6 +44,10 @@ def test_poly_asserts():
     C.case_poly_asserts()
 
 
+def test_poly_split_recursion():
+    C.case_poly_split_recursion()
+
+
 def test_fast_multiply_4096():
     C.case_fast_multiply_big(1 << 12)
 

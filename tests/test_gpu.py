@@ -365,6 +365,10 @@ def test_dropin_poly(eng):
     C.case_poly_asserts()
 
 
+def test_dropin_poly_split_recursion(eng):
+    C.case_poly_split_recursion()
+
+
 def test_dropin_fast_multiply_digests(eng):
     C.case_fast_multiply_big(1 << 12)
     C.case_fast_multiply_big(1 << 20)  # BASELINE.md section 3 (654 s of reference time)
