@@ -125,26 +125,6 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def _cpus_next_to_gpu(torch, index):
-    """CPUs of the NUMA node the GPU's PCIe root hangs off (sysfs local_cpulist), or None"""
-    try:
-        pr = torch.cuda.get_device_properties(index)
-        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
-            text = f.read().strip()
-        cpus = set()
-        for part in text.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        cpus &= os.sched_getaffinity(0)
-        return cpus or None
-    except (OSError, AttributeError, ValueError):
-        return None
-
-
 def run_ours(args):
     import numpy as np
     import torch
@@ -247,32 +227,32 @@ def run_ours(args):
     single_us = ev2.elapsed_time(ev3) / reps * 1e3
 
     # ---- e2e: the same step through the C-ABI host entry (pinned host buffers, H2D + D2H inside)
-    # The caller owns the host buffers: like a launcher that starts each rank under numactl, allocate them
-    # while running on the CPUs next to this rank's GPU, so the pinned pages sit on that NUMA node and
-    # eight ranks do not push half of their copies across the socket interconnect.
-    all_cpus = os.sched_getaffinity(0)
-    near = _cpus_next_to_gpu(torch, local)
-    if near:
-        os.sched_setaffinity(0, near)
-    hx = torch.empty_like(x, device="cpu").pin_memory()
-    hy = torch.empty_like(x, device="cpu").pin_memory()
-    hx.copy_(x)
-    hy.zero_()
+    # The host buffers come from the library's own allocator (sa_host_alloc: page-locked, placed on the NUMA
+    # node of this rank's GPU, so eight ranks do not push half of their copies across the socket interconnect).
+    nbytes = BATCH * N * 16
+    p_in, p_out = lib.sa_host_alloc(nbytes), lib.sa_host_alloc(nbytes)
+    assert p_in and p_out, lib.sa_last_error()
+    hx = np.ctypeslib.as_array((ctypes.c_uint64 * (nbytes // 8)).from_address(p_in)).reshape(-1, 2)
+    hy = np.ctypeslib.as_array((ctypes.c_uint64 * (nbytes // 8)).from_address(p_out)).reshape(-1, 2)
+    hx[:] = x.cpu().numpy().view(np.uint64)
+    hy[:] = 0
     e2e_steps = max(2, min(args.steps, 5))
-    lib.sa_ntt_host(hy.data_ptr(), hx.data_ptr(), LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
+    lib.sa_ntt_host(p_out, p_in, LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rc = lib.sa_ntt_host(hy.data_ptr(), hx.data_ptr(), LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
+        rc = lib.sa_ntt_host(p_out, p_in, LOG_N, root, 0, BATCH, ctypes.c_void_p(stream.cuda_stream))
         assert rc == 0
     torch.cuda.synchronize()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * BATCH * BUTTERFLIES_PER_NTT / float(e2e_s.item())
-    os.sched_setaffinity(0, all_cpus)
     if rank == 0:
-        assert (hy[:N].numpy().view(np.uint64) == want).all(), "e2e output differs from the oracle"
+        assert (hy[:N] == want).all(), "e2e output differs from the oracle"
+    del hx, hy
+    lib.sa_host_free(p_in)
+    lib.sa_host_free(p_out)
 
     # ---- FRI commit ms @ 2^20 (second half of BASELINE.json's metric), rank 0 only, list API excluded:
     #      device-resident codeword, 12 fused rounds, host Fiat-Shamir on the 64-byte roots
@@ -388,8 +368,8 @@ def run_ours(args):
                        "sample": "oracle.py py_ntt at n = 2^12; the reference's own ntt measured 3.9e4-6.4e4 "
                                  "butterflies/s at 2^10..2^20 on one Xeon core (BASELINE.md section 2)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * 16,
-                "d2h_bytes_per_step": BATCH * N * 16, "api": "sa_ntt_host (C ABI, pinned host buffers)",
-                "host_buffers": "pinned, allocated on the NUMA node of the rank's GPU" if near else "pinned"},
+                "d2h_bytes_per_step": BATCH * N * 16, "api": "sa_ntt_host (C ABI, host buffers from sa_host_alloc)",
+                "host_buffers": "page-locked, on the NUMA node of the rank's GPU (sa_host_alloc)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "single_ntt_us": single_us,

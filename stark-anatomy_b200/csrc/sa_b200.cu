@@ -4,8 +4,11 @@
 // Reference behaviour reproduced (bit-exact): code/ntt.py:3-30,61,133,172, code/fri.py:85,
 // code/merkle.py:6-27, code/algebra.py:53-57,75-94.
 #include <cuda_runtime.h>
+#include <pthread.h>
+#include <sched.h>
 
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -803,6 +806,60 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     }
     SA_CUDA(cudaStreamSynchronize(st));
     return rc;
+}
+
+// ---- pinned host buffers next to the GPU ----
+static bool gpu_local_cpus(cpu_set_t *set) {
+    int dev = 0;
+    char bdf[32] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bdf, sizeof(bdf), dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char *c = bdf; *c; c++) *c = (char)tolower((unsigned char)*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char text[4096] = {0};
+    const size_t got = fread(text, 1, sizeof(text) - 1, f);
+    fclose(f);
+    if (got == 0) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char *tok = strtok(text, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++, count++) CPU_SET(c, set);
+    }
+    return count > 0;
+}
+
+void *sa_host_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    cpu_set_t before, near, both;
+    const bool have_before = pthread_getaffinity_np(pthread_self(), sizeof(before), &before) == 0;
+    bool moved = false;
+    if (have_before && gpu_local_cpus(&near)) {
+        CPU_AND(&both, &before, &near);
+        if (CPU_COUNT(&both) > 0) moved = pthread_setaffinity_np(pthread_self(), sizeof(both), &both) == 0;
+    }
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);  // pages are placed now, here
+    if (e == cudaSuccess) memset(p, 0, bytes);
+    if (moved) pthread_setaffinity_np(pthread_self(), sizeof(before), &before);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("sa_host_alloc: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+int sa_host_free(void *p) {
+    if (p) SA_CUDA(cudaFreeHost(p));
+    return SA_OK;
 }
 
 static inline unsigned grid_for(long long n, int bs, long long cap = 148 * 16) {

@@ -37,6 +37,8 @@ SYMBOLS = [
     ("sa_launch_count", ctypes.c_uint64, []),
     ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_host_alloc", _vp, [_sz]),
+    ("sa_host_free", _ci, [_vp]),
     ("sa_pointwise_mul", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_pointwise_div", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_scale", _ci, [_vp, _vp, _sz, _u64p, _vp]),

@@ -23,6 +23,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.sa_version().startswith(b"sa_b200")
 
 
+def test_host_alloc_without_a_gpu_fails_loudly():
+    """sa_host_alloc needs the CUDA runtime for page-locked memory: on a box without a GPU it returns
+    NULL and says why (there is no quiet fallback to malloc); with a GPU the buffer is usable"""
+    G.build_cuda()
+    G._paths()
+    import sa_engine
+    lib = sa_engine.load_library()
+    p = lib.sa_host_alloc(1 << 20)
+    if p is None:
+        assert b"sa_host_alloc" in lib.sa_last_error()
+    else:
+        ctypes.memset(p, 0x5A, 1 << 20)
+        assert lib.sa_host_free(p) == 0
+    assert lib.sa_host_free(None) == 0
+
+
 def test_marshal_roundtrip_and_pickle_identity():
     import pickle
     import random

@@ -154,15 +154,24 @@ def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
     w = O.primitive_nth_root(n)
     x = rand_np(1200 + log_n, n * batch)
     want = O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2)
-    hx = torch.from_numpy(x.view(np.int64)).pin_memory()
-    hy = torch.empty_like(hx).pin_memory()
-    for inverse in (0, 1):
-        src = hx if not inverse else hy
-        rc = eng.lib.sa_ntt_host(hy.data_ptr(), src.data_ptr(), log_n, sa_engine._limbs(w), inverse, batch, eng._stream())
-        assert rc == 0
-        if not inverse:
-            assert (hy.numpy().view(np.uint64) == want).all()
-    assert (hy.numpy().view(np.uint64) == x).all()  # in-place inverse through the same pipeline
+    # buffers from the library's allocator (page-locked, on the GPU's NUMA node)
+    nbytes = x.nbytes
+    p_in, p_out = eng.lib.sa_host_alloc(nbytes), eng.lib.sa_host_alloc(nbytes)
+    assert p_in and p_out, eng.lib.sa_last_error()
+    try:
+        hx = np.ctypeslib.as_array((ctypes.c_uint64 * (nbytes // 8)).from_address(p_in)).reshape(-1, 2)
+        hy = np.ctypeslib.as_array((ctypes.c_uint64 * (nbytes // 8)).from_address(p_out)).reshape(-1, 2)
+        hx[:] = x
+        for inverse in (0, 1):
+            src = p_in if not inverse else p_out
+            rc = eng.lib.sa_ntt_host(p_out, src, log_n, sa_engine._limbs(w), inverse, batch, eng._stream())
+            assert rc == 0
+            if not inverse:
+                assert (hy == want).all()
+        assert (hy == x).all()  # in-place inverse through the same pipeline
+        del hx, hy
+    finally:
+        assert eng.lib.sa_host_free(p_in) == 0 and eng.lib.sa_host_free(p_out) == 0
 
 
 def test_ntt_two_streams_and_threads(eng):
