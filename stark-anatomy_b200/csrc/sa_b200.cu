@@ -708,33 +708,52 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
 // of chunk i-1 overlap (PCIe is full duplex); with pinned host buffers the call is bound by the
 // slower copy direction instead of the sum of both.
 constexpr int HOST_STREAMS_MAX = 8;
-static cudaStream_t g_copy_streams[HOST_STREAMS_MAX];
-static cudaEvent_t g_copy_events[HOST_STREAMS_MAX + 1];
+// one set of copy streams (and of the device buffers that go with them) per device; a set is used by
+// one sa_ntt_host call at a time - the link is the shared resource anyway
+struct CopySet {
+    cudaStream_t streams[HOST_STREAMS_MAX];
+    cudaEvent_t events[HOST_STREAMS_MAX + 1];
+    std::mutex busy;
+};
+static std::map<int, CopySet *> g_copy_sets;
+static std::mutex g_copy_mu;
 static int g_host_streams = 4;            // SA_HOST_STREAMS
 static size_t g_host_chunk = 32u << 20;   // SA_HOST_CHUNK_MIB: bytes per pipelined chunk
 static int g_host_ramp = 1;               // SA_HOST_RAMP: first/last chunks start at chunk >> ramp
 // (measured, profiles/r01g_e2e_pipeline_sweep.txt: 4 streams x 32 MiB with a one-step ramp 6.35 ms per
 //  16 x 2^20 call, 3 x 16 MiB flat 6.48-6.58 ms; the link does 49.6 GB/s each way on monolithic copies)
-static int copy_streams_ready() {
-    static bool ready = false;
-    if (ready) return SA_OK;
-    if (const char *e = getenv("SA_HOST_STREAMS")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= HOST_STREAMS_MAX) g_host_streams = v;
+static int get_copy_set(CopySet **out) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_copy_mu);
+    auto it = g_copy_sets.find(dev);
+    if (it != g_copy_sets.end()) {
+        *out = it->second;
+        return SA_OK;
     }
-    if (const char *e = getenv("SA_HOST_CHUNK_MIB")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 1024) g_host_chunk = (size_t)v << 20;
+    static bool configured = false;
+    if (!configured) {
+        configured = true;
+        if (const char *e = getenv("SA_HOST_STREAMS")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= HOST_STREAMS_MAX) g_host_streams = v;
+        }
+        if (const char *e = getenv("SA_HOST_CHUNK_MIB")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 1024) g_host_chunk = (size_t)v << 20;
+        }
+        if (const char *e = getenv("SA_HOST_RAMP")) {
+            const int v = atoi(e);
+            if (v >= 0 && v <= 6) g_host_ramp = v;
+        }
     }
-    if (const char *e = getenv("SA_HOST_RAMP")) {
-        const int v = atoi(e);
-        if (v >= 0 && v <= 6) g_host_ramp = v;
-    }
+    CopySet *set = new CopySet();
     for (int i = 0; i < g_host_streams; i++)
-        SA_CUDA(cudaStreamCreateWithFlags(&g_copy_streams[i], cudaStreamNonBlocking));
+        SA_CUDA(cudaStreamCreateWithFlags(&set->streams[i], cudaStreamNonBlocking));
     for (int i = 0; i <= g_host_streams; i++)
-        SA_CUDA(cudaEventCreateWithFlags(&g_copy_events[i], cudaEventDisableTiming));
-    ready = true;
+        SA_CUDA(cudaEventCreateWithFlags(&set->events[i], cudaEventDisableTiming));
+    g_copy_sets[dev] = set;
+    *out = set;
     return SA_OK;
 }
 
@@ -746,7 +765,8 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     const size_t bytes = one * batch;
     if (bytes == 0) return SA_OK;
     int rc;
-    if ((rc = copy_streams_ready()) != SA_OK) return rc;
+    CopySet *cset = nullptr;
+    if ((rc = get_copy_set(&cset)) != SA_OK) return rc;
     // chunk = as many transforms as fit g_host_chunk (default two 2^20 transforms); small jobs stay on `st`
     size_t per_chunk = one >= g_host_chunk ? 1 : g_host_chunk / one;
     if (per_chunk > batch) per_chunk = batch;
@@ -761,6 +781,9 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
         return rc;
     }
     const int ns = g_host_streams;
+    std::lock_guard<std::mutex> one_call_at_a_time(cset->busy);
+    cudaStream_t *g_copy_streams = cset->streams;
+    cudaEvent_t *g_copy_events = cset->events;
     // chunk sizes (in transforms): ramp up from a small first chunk and down to a small last one, so
     // that the stretch where only one copy direction is busy (before the first kernel can start, after
     // the last one has finished) is short while the bulk moves in few large copies

@@ -174,6 +174,30 @@ def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
         assert eng.lib.sa_host_free(p_in) == 0 and eng.lib.sa_host_free(p_out) == 0
 
 
+def test_ntt_host_entry_from_two_threads(eng):
+    """two host threads in sa_ntt_host at once: the copy streams and their device buffers belong to one
+    call at a time (per-device mutex), so both results must still be exact"""
+    import threading
+    log_n, batch = 18, 12  # 48 MiB per call: several pipelined chunks
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    xs = [rand_np(1300 + i, n * batch) for i in range(2)]
+    outs = [np.zeros_like(xs[0]), np.zeros_like(xs[1])]
+    rcs = [None, None]
+
+    def work(i):
+        for _ in range(3):
+            rcs[i] = eng.lib.sa_ntt_host(outs[i].ctypes.data, xs[i].ctypes.data, log_n, sa_engine._limbs(w), 0, batch, None)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for i in range(2):
+        assert rcs[i] == 0
+        assert (outs[i] == O.ntt_batch_np(w, xs[i].reshape(batch, n, 2)).reshape(-1, 2)).all()
+
+
 def test_ntt_two_streams_and_threads(eng):
     """independent work on two CUDA streams from two host threads (per-stream workspaces, shared
     plan cache behind a mutex): results equal the oracle's"""
