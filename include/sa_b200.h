@@ -20,7 +20,10 @@
  *  - No torch types, no C++ types: plain pointers and sizes.
  *  - Thread safety: entry points may be called from several host threads; the
  *    twiddle/plan caches are guarded by a mutex.  Work submitted to different
- *    streams is independent.
+ *    streams is independent (scratch buffers and the Merkle arrival counter are per
+ *    device and stream); two threads must not be inside calls on the SAME stream at
+ *    the same time.  sa_ntt_host calls on one device run one after the other
+ *    (they share the copy streams - and the PCIe link).
  */
 #ifndef SA_B200_H
 #define SA_B200_H
