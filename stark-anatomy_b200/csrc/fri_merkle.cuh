@@ -41,7 +41,7 @@ struct MerkleArgs {
 };
 
 // launch shape for a level of `width` bottom nodes: small levels are latency bound (one node per
-// thread, as many CTAs as possible, each CTA reducing its chunk to one digest); big ones are
+// thread, 64..256-node CTAs so that 128-256 CTAs are in flight, each reducing its chunk to one digest); big ones are
 // throughput bound: four leaves and their three parents per thread, barrier free, then only the three
 // shared-memory levels that still fill whole warps (128, 64, 32 nodes) - the 32 digests a CTA leaves
 // are picked up by the next launch, so no SM sits in a mostly idle dependency chain while thousands
@@ -53,11 +53,18 @@ SA_HD int merkle_log2(long long x) {
 }
 SA_HD void merkle_shape(MerkleArgs &a) {
     a.coop_max = MK_THREADS / 4;  // latency bound: a level of <= 64 nodes keeps all 256 lanes busy that way
-    if (a.width <= MK_THREADS) {  // one CTA finishes the tree
-        a.ipt_log = 0;
+    a.ipt_log = 0;
+    if (a.width <= 64) {  // one CTA finishes the tree
         a.chunk = (int)a.width;
-    } else if (a.width < (1 << 17)) {  // <= one wave of 256-node CTAs: shortest dependency chain
-        a.ipt_log = 0;
+    } else if (a.width < (1 << 14)) {
+        // dependency-chain regime, measured (profiles/r01g_merkle_small_shapes.txt): few leaves per CTA
+        // spread the leaf hashes (a warp-wide compression occupies its scheduler for 2.3 us whatever
+        // the number of active lanes) over many SMs, and the CTA that arrives last reduces the <= 256
+        // subtree roots, so the tree is still one launch
+        a.chunk = 64;
+    } else if (a.width < (1 << 15)) {
+        a.chunk = 128;
+    } else if (a.width < (1 << 16)) {
         a.chunk = MK_THREADS;
     } else if (a.width < (1 << 18)) {
         a.ipt_log = 1;

@@ -124,7 +124,7 @@ def test_decimal_and_leaf(E):
         assert d.tobytes() == hashlib.blake2b(l + r).digest()  # four-lanes-per-node schedule
 
 
-@pytest.mark.parametrize("logn", [0, 1, 2, 5, 8, 9, 10, 11, 12, 15, 16])
+@pytest.mark.parametrize("logn", [0, 1, 2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17])
 def test_merkle_and_fri_round(E, logn):
     rng = random.Random(40 + logn)
     n = 1 << logn

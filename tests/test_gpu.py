@@ -298,7 +298,7 @@ def test_zerofier_and_interpolate(eng, k):
             eng.interpolate(up(eng, dom), up(eng, vals))
 
 
-@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 9, 10, 11, 14, 17])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 6, 7, 9, 10, 11, 13, 14, 15, 16, 17, 18])
 def test_merkle_tree_and_open(eng, log_n):
     n = 1 << log_n
     x = rand_np(50 + log_n, n)
@@ -328,7 +328,7 @@ def test_merkle_root_2_20_golden(eng):
     assert eng.tree_root(tree).hex() == c["root"]
 
 
-@pytest.mark.parametrize("log_n", [1, 2, 6, 10, 11, 15])
+@pytest.mark.parametrize("log_n", [1, 2, 6, 7, 8, 10, 11, 14, 15, 16, 17, 18])
 def test_fri_round_and_fold(eng, log_n):
     n = 1 << log_n
     x = rand_np(60 + log_n, n)
