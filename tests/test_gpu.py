@@ -111,6 +111,41 @@ def test_ntt_2_24_roundtrip_in_place(eng):
         eng.ntt(eng.empty(16), 27, w)
 
 
+def test_ntt_2_26_maximum_size(eng):
+    """the largest supported transform (three passes, 1 GiB per vector): a unit impulse at j must come out
+    as c * w^(i*j) (checked at sampled indices with host pow), the all-ones vector as n * e_0, and a random
+    vector must survive the round trip - no oracle run at this size"""
+    import torch
+    log_n = 26
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    root = sa_engine._limbs(w)
+    rng = random.Random(26)
+    j, c = rng.randrange(n), rng.randrange(1, P)
+    v = eng.zeros(n)
+    s64 = lambda u: u - (1 << 64) if u >= (1 << 63) else u  # limb as the int64 torch stores
+    v[j, 0] = s64(c & 0xFFFFFFFFFFFFFFFF)
+    v[j, 1] = s64(c >> 64)
+    out = eng.empty(n)
+    assert eng.lib.sa_ntt(out.data_ptr(), v.data_ptr(), log_n, root, 0, 1, eng._stream()) == 0
+    idx = [0, 1, n - 1, n // 2] + [rng.randrange(n) for _ in range(500)]
+    got = eng.gather(out, idx).view(np.uint64)
+    for k, i in enumerate(idx):
+        want = c * pow(w, (i * j) % n, P) % P
+        assert int(got[k][0]) | (int(got[k][1]) << 64) == want, i
+    v.zero_()
+    v[:, 0] = 1
+    assert eng.lib.sa_ntt(out.data_ptr(), v.data_ptr(), log_n, root, 0, 1, eng._stream()) == 0
+    assert int(out[0, 0]) == n and int(out[0, 1]) == 0 and not bool(out[1:].any())
+    del v
+    x = torch.randint(0, 1 << 62, (n, 2), dtype=torch.int64, device=eng.device)
+    x[:, 1] &= (1 << 61) - 1
+    ref = x.clone()
+    assert eng.lib.sa_ntt(x.data_ptr(), x.data_ptr(), log_n, root, 0, 1, eng._stream()) == 0
+    assert eng.lib.sa_ntt(x.data_ptr(), x.data_ptr(), log_n, root, 1, 1, eng._stream()) == 0
+    assert bool((x == ref).all())
+
+
 def test_ntt_edge_inputs_and_roots(eng):
     for log_n in (3, 10, 13):
         n = 1 << log_n
