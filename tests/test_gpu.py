@@ -354,6 +354,63 @@ def test_merkle_tree_and_open(eng, log_n):
             eng.merkle_open(tree, [n])
 
 
+def test_merkle_tree_2_22_composes_from_halves(eng):
+    """beyond the oracle's reach: the root over 2^22 leaves must be blake2b(root(left half) || root(right
+    half)), every level-1 node of the big tree must be the root of the corresponding half, and an opened
+    path must hash back to the root"""
+    import hashlib
+    import torch
+    n = 1 << 22
+    x = torch.randint(0, 1 << 62, (n, 2), dtype=torch.int64, device=eng.device)
+    x[:, 1] &= (1 << 61) - 1
+    big = eng.merkle_tree(x)
+    left, right = eng.merkle_tree(x[:n // 2]), eng.merkle_tree(x[n // 2:])
+    rl, rr = eng.tree_root(left), eng.tree_root(right)
+    assert bytes(big[2].cpu().numpy().tobytes()) == rl and bytes(big[3].cpu().numpy().tobytes()) == rr
+    assert eng.tree_root(big) == hashlib.blake2b(rl + rr).digest()
+    i = 2718281
+    path = eng.merkle_open(big, [i])[0]
+    v = eng.gather(x, [i]).view(np.uint64)[0]
+    acc = hashlib.blake2b(str(int(v[0]) | (int(v[1]) << 64)).encode()).digest()
+    k = i
+    for sib in path:
+        acc = hashlib.blake2b(sib + acc if k & 1 else acc + sib).digest()
+        k >>= 1
+    assert acc == eng.tree_root(big)
+
+
+def test_fri_commit_2_22_layers_fold_correctly(eng):
+    """14 rounds on a 2^22 codeword (four times the golden case): every layer must be the split-and-fold
+    of the previous one (fri.py:85, checked at sampled indices with host integers) and every published
+    root must be node 1 of the retained tree"""
+    import torch
+    n, rounds = 1 << 22, 14
+    omega, off = O.primitive_nth_root(n), O.GENERATOR
+    rng = random.Random(2222)
+    alphas = [rng.randrange(P) for _ in range(rounds)]
+    cw = torch.randint(0, 1 << 62, (n, 2), dtype=torch.int64, device=eng.device)
+    cw[:, 1] &= (1 << 61) - 1
+    roots = []
+    layers, trees = eng.fri_commit(cw, rounds, off, omega, lambda r, root, want: (roots.append(root), alphas[r])[1])
+    assert len(layers) == rounds and len(roots) == rounds
+    inv2 = pow(2, P - 2, P)
+    val = lambda row: int(row[0]) | (int(row[1]) << 64)
+    o, w, ln = off, omega, n
+    for r in range(rounds):
+        assert eng.tree_root(trees[r]) == roots[r]
+        if r + 1 < rounds:
+            half = ln // 2
+            idx = [0, half - 1] + [rng.randrange(half) for _ in range(30)]
+            a = eng.gather(layers[r], idx).view(np.uint64)
+            b = eng.gather(layers[r], [i + half for i in idx]).view(np.uint64)
+            c = eng.gather(layers[r + 1], idx).view(np.uint64)
+            for k, i in enumerate(idx):
+                t = alphas[r] * pow(o * pow(w, i, P) % P, P - 2, P) % P
+                want = inv2 * ((1 + t) * val(a[k]) + (1 - t) * val(b[k])) % P
+                assert val(c[k]) == want, (r, i)
+            o, w, ln = o * o % P, w * w % P, half
+
+
 def test_merkle_root_2_20_golden(eng):
     from conftest import load_golden
     c = [m for m in load_golden("merkle.json")["commit"] if m["n"] == 1 << 20][0]
