@@ -820,6 +820,10 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
         // within one stream the copies and kernels of successive chunks are ordered, so one device
         // buffer per stream is enough; different streams overlap upload, kernels and download
         SA_CUDA(cudaMemcpyAsync(buf[si], src, cnt * one, cudaMemcpyHostToDevice, cs));
+#ifdef SA_TUNE
+        static const bool skip_ntt = getenv("SA_HOST_SKIP_NTT") != nullptr;  // copy pipeline alone (diagnostic)
+        if (!skip_ntt)
+#endif
         rc = sa_ntt(buf[si], buf[si], log_n, root, inverse, cnt, (void *)cs);
         if (rc == SA_OK) SA_CUDA(cudaMemcpyAsync(dst, buf[si], cnt * one, cudaMemcpyDeviceToHost, cs));
     }
