@@ -59,7 +59,7 @@ uint64_t sa_launch_count(void);
  * contiguous transforms of n = 2^log_n elements.  inverse != 0 computes intt: the
  * transform with root^-1 followed by the multiplication with n^-1.
  * Validates root^n == 1 and root^(n/2) != 1 exactly like the reference's asserts.
- * in == out is allowed.  log_n in [0, 30].                                              */
+ * in == out is allowed.  log_n in [0, 26].                                               */
 int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
            void *stream);
 /* Same through HOST buffers: H2D copy, transforms, D2H copy, synchronises before
