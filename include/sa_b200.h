@@ -19,7 +19,7 @@
  *    the corresponding reference function raises.
  *  - No torch types, no C++ types: plain pointers and sizes.
  *  - Thread safety: entry points may be called from several host threads; the
- *    twiddle/plan caches are guarded by a mutex.  Work submitted to different
+ *    twiddle/plan caches are guarded by a mutex (tables are built outside of it).  Work submitted to different
  *    streams is independent (scratch buffers and the Merkle arrival counter are per
  *    device and stream); two threads must not be inside calls on the SAME stream at
  *    the same time.  sa_ntt_host calls on one device run one after the other
@@ -135,6 +135,19 @@ typedef int (*sa_fri_challenge_fn)(void *user, int round, const uint8_t root[64]
 int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int rounds,
                   const uint64_t offset[2], const uint64_t omega[2], sa_fri_challenge_fn challenge, void *user,
                   void *stream);
+
+/* ---- device memory the library keeps between calls (no reference counterpart) ------------------
+ * Twiddle tables (per device, log n, root, direction) and FRI x^-1 tables (per device, omega, n)
+ * live in one least-recently-used cache bounded by bytes: default 4 GiB, SA_CACHE_LIMIT_MIB, or
+ * sa_cache_limit(bytes), which also evicts down to the new limit right away and returns the bytes
+ * still cached (sa_cache_limit(0) drops everything).  A table in use by an enqueued kernel is freed
+ * only after that kernel has finished.  sa_cache_bytes() = bytes cached now.
+ * sa_release_workspaces() synchronises the current device and frees its per-stream scratch buffers
+ * (the n * batch intermediate of the multi-pass transforms, host-entry staging), which otherwise
+ * only grow.                                                                                */
+size_t sa_cache_limit(size_t bytes);
+size_t sa_cache_bytes(void);
+int sa_release_workspaces(void);
 
 /* ---- self checks (used by tests / smoke) ------------------------------------------------
  * Runs the sm_100a carry-chain field arithmetic against the portable C++ version on

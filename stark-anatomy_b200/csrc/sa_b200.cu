@@ -7,6 +7,7 @@
 #include <pthread.h>
 #include <sched.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cctype>
 #include <chrono>
@@ -14,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -477,20 +479,105 @@ static void keep_pool_memory() {
 }
 
 // ---------------------------------------------------------------- NTT plans --
-struct NttPlan {
+// Twiddle tables are cached per (device, log n, root, direction); FRI x^-1 tables per (device, omega, n).
+// Both live in one LRU bounded by bytes (sa_cache_limit): fast_multiply's order shrinking
+// (ntt.py:47-49) and a prover that walks through many domains generate new roots all the time, and
+// a 2^20 plan holds a 16 MiB inter-pass matrix.  Entries are handed out as shared_ptr: an evicted
+// table is freed when its last user lets go, and cudaFree waits for kernels still reading it.
+struct DeviceTables {
+    std::vector<void *> ptrs;
+    size_t bytes = 0;
+    int device = 0;
+    int alloc(void **out, size_t nbytes) {
+        SA_CUDA(cudaMalloc(out, nbytes));
+        ptrs.push_back(*out);
+        bytes += nbytes;
+        return SA_OK;
+    }
+    ~DeviceTables() {
+        if (ptrs.empty()) return;
+        int cur = 0;
+        const bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+        for (void *p : ptrs) cudaFree(p);
+        if (sw) cudaSetDevice(cur);
+        cudaGetLastError();
+    }
+};
+struct NttPlan : DeviceTables {
     int log_n = 0, l1 = 0, l2 = 0, l3 = 0;
     fe *tw1 = nullptr, *tw2 = nullptr, *tw3 = nullptr, *twb = nullptr, *twb2 = nullptr;
     fe cst1[8], cst2[8], cst3[8];
     fe scale_m;     // n^-1 (Montgomery) for single-tile inverse transforms
     int has_scale = 0;
 };
-using PlanKey = std::tuple<int, int, uint64_t, uint64_t, int>;  // device, log_n, root lo, root hi, inverse
+struct XinvTable : DeviceTables {
+    fe *tab = nullptr;
+};
+using PlanPtr = std::shared_ptr<NttPlan>;
+using XinvPtr = std::shared_ptr<XinvTable>;
+// kind (0 plan, 1 xinv), device, log_n | n, root lo, root hi, inverse
+using CacheKey = std::tuple<int, int, uint64_t, uint64_t, uint64_t, int>;
+struct CacheEntry {
+    std::shared_ptr<DeviceTables> tables;
+    uint64_t tick = 0;
+};
 static std::mutex g_plan_mu;
-static std::map<PlanKey, NttPlan> g_plans;
+static std::map<CacheKey, CacheEntry> g_cache;
+static size_t g_cache_bytes = 0;
+static size_t g_cache_limit = (size_t)4 << 30;  // bytes; SA_CACHE_LIMIT_MIB / sa_cache_limit()
+static uint64_t g_cache_tick = 0;
 
-static int build_pow_table(fe **out, const fe &base_m, const fe &lead_m, long long count, cudaStream_t st,
-                           int swz = 0) {
-    SA_CUDA(cudaMalloc(out, sizeof(fe) * (size_t)count));
+static void cache_config() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char *e = getenv("SA_CACHE_LIMIT_MIB")) {
+            const long long v = atoll(e);
+            if (v >= 0) g_cache_limit = (size_t)v << 20;
+        }
+    });
+}
+// g_plan_mu held.  Drops least-recently-used entries until `incoming` more bytes fit (an entry larger
+// than the whole limit is still admitted alone: the call that needs it has to run).
+static void cache_make_room(size_t incoming) {
+    while (!g_cache.empty() && g_cache_bytes + incoming > g_cache_limit) {
+        auto victim = g_cache.begin();
+        for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+            if (it->second.tick < victim->second.tick) victim = it;
+        g_cache_bytes -= victim->second.tables->bytes;
+        g_cache.erase(victim);  // frees the device memory once nobody holds the tables any more
+    }
+}
+template <class T>
+static std::shared_ptr<T> cache_find(const CacheKey &key) {
+    cache_config();
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) return nullptr;
+    it->second.tick = ++g_cache_tick;
+    return std::static_pointer_cast<T>(it->second.tables);
+}
+// publishes `made` unless another thread got there first (then that one wins and `made` is dropped)
+template <class T>
+static std::shared_ptr<T> cache_publish(const CacheKey &key, std::shared_ptr<T> made) {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        it->second.tick = ++g_cache_tick;
+        return std::static_pointer_cast<T>(it->second.tables);
+    }
+    cache_make_room(made->bytes);
+    CacheEntry e;
+    e.tables = made;
+    e.tick = ++g_cache_tick;
+    g_cache.emplace(key, e);
+    g_cache_bytes += made->bytes;
+    return made;
+}
+
+static int build_pow_table(DeviceTables &owner, fe **out, const fe &base_m, const fe &lead_m, long long count,
+                           cudaStream_t st, int swz = 0) {
+    int rc = owner.alloc((void **)out, sizeof(fe) * (size_t)count);
+    if (rc != SA_OK) return rc;
     const long long threads = (count + 15) / 16;
     const int bs = 128;
     k_pow_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(*out, base_m, lead_m, count, swz);
@@ -498,19 +585,15 @@ static int build_pow_table(fe **out, const fe &base_m, const fe &lead_m, long lo
     return SA_OK;
 }
 
-// validates the root like ntt.py:10-11 and returns (creating if needed) the plan
-static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, cudaStream_t st) {
+// validates the root like ntt.py:10-11 and returns (creating if needed) the plan.  Tables are built
+// outside the cache lock; a failed build frees what it had allocated (the plan object owns them).
+static int get_plan(PlanPtr *plan_out, int log_n, const fe &root, int inverse, cudaStream_t st) {
     int dev = 0;
     SA_CUDA(cudaGetDevice(&dev));
     const uint64_t rlo = (uint64_t)root.v[0] | ((uint64_t)root.v[1] << 32);
     const uint64_t rhi = (uint64_t)root.v[2] | ((uint64_t)root.v[3] << 32);
-    const PlanKey key(dev, log_n, rlo, rhi, inverse ? 1 : 0);
-    std::lock_guard<std::mutex> lock(g_plan_mu);
-    auto it = g_plans.find(key);
-    if (it != g_plans.end()) {
-        *plan_out = &it->second;
-        return SA_OK;
-    }
+    const CacheKey key(0, dev, (uint64_t)log_n, rlo, rhi, inverse ? 1 : 0);
+    if ((*plan_out = cache_find<NttPlan>(key))) return SA_OK;
     const uint64_t n = 1ull << log_n;
     const fe root_m = fe_to_mont(root);
     if (!fe_eq(fe_mont_pow_u64(root_m, n), fe_mont_one())) return SA_EROOTORDER;
@@ -518,7 +601,9 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
     // the transform root: root itself, or root^-1 for intt (ntt.py:29)
     const fe w_m = inverse ? fe_mont_inv(root_m) : root_m;
     const fe ninv_m = fe_mont_inv(fe_to_mont(fe_from_u64(n)));  // ntt.py:27
-    NttPlan p;
+    PlanPtr made = std::make_shared<NttPlan>();
+    NttPlan &p = *made;
+    p.device = dev;
     p.log_n = log_n;
     int rc;
     const NttShape shape = ntt_shape(log_n);
@@ -532,14 +617,14 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         const fe wsub_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-m sub-transforms
         const fe w2_m = fe_mont_pow_u64(wsub_m, (uint64_t)n3);
         const fe w3_m = fe_mont_pow_u64(wsub_m, (uint64_t)n2);
-        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw3, w3_m, fe_mont_one(), n3, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw3, w3_m, fe_mont_one(), n3, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w1_m, n1);
         ntt_fill_cst(p.cst2, w2_m, n2);
         ntt_fill_cst(p.cst3, w3_m, n3);
-        SA_CUDA(cudaMalloc(&p.twb, sizeof(fe) * (size_t)n));
-        SA_CUDA(cudaMalloc(&p.twb2, sizeof(fe) * (size_t)m));
+        if ((rc = p.alloc((void **)&p.twb, sizeof(fe) * (size_t)n)) != SA_OK) return rc;
+        if ((rc = p.alloc((void **)&p.twb2, sizeof(fe) * (size_t)m)) != SA_OK) return rc;
         const int bs = 128;
         long long threads = (long long)n1 * ((m + 15) / 16);
         k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(p.twb, w_m, inverse ? ninv_m : fe_mont_one(),
@@ -549,7 +634,7 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(p.twb2, wsub_m, fe_mont_one(), n2, n3);
         SA_LAUNCH_CHECK();
     } else if (log_n <= 10) {
-        if ((rc = build_pow_table(&p.tw1, w_m, fe_mont_one(), (long long)n, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw1, w_m, fe_mont_one(), (long long)n, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w_m, (int)n);
         p.has_scale = inverse ? 1 : 0;
         p.scale_m = inverse ? ninv_m : fe_mont_one();
@@ -557,11 +642,11 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
         const int n1 = 1 << p.l1, n2 = 1 << p.l2;
         const fe w1_m = fe_mont_pow_u64(w_m, (uint64_t)n2);  // root of the length-n1 column transforms
         const fe w2_m = fe_mont_pow_u64(w_m, (uint64_t)n1);  // root of the length-n2 row transforms
-        if ((rc = build_pow_table(&p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
-        if ((rc = build_pow_table(&p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw1, w1_m, fe_mont_one(), n1, st, 1)) != SA_OK) return rc;
+        if ((rc = build_pow_table(p, &p.tw2, w2_m, fe_mont_one(), n2, st, 1)) != SA_OK) return rc;
         ntt_fill_cst(p.cst1, w1_m, n1);
         ntt_fill_cst(p.cst2, w2_m, n2);
-        SA_CUDA(cudaMalloc(&p.twb, sizeof(fe) * (size_t)n));
+        if ((rc = p.alloc((void **)&p.twb, sizeof(fe) * (size_t)n)) != SA_OK) return rc;
         const long long threads = (long long)n1 * ((n2 + 15) / 16);
         const int bs = 128;
         k_twb_table<<<(unsigned)((threads + bs - 1) / bs), bs, 0, st>>>(
@@ -571,8 +656,20 @@ static int get_plan(NttPlan **plan_out, int log_n, const fe &root, int inverse, 
     // the tables were built on `st`; other streams may pick the plan up from the cache right away,
     // so they must be complete before it is published (one-time cost per plan)
     SA_CUDA(cudaStreamSynchronize(st));
-    auto ins = g_plans.emplace(key, p);
-    *plan_out = &ins.first->second;
+    *plan_out = cache_publish<NttPlan>(key, made);
+    return SA_OK;
+}
+
+// kernels with more than 48 KB of dynamic shared memory need the opt-in once per (kernel, device)
+constexpr int SA_MAX_DEVICES = 64;
+template <class K>
+static int optin_smem(K kernel, std::atomic<bool> *done, size_t smem) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= SA_MAX_DEVICES || !done[dev].load(std::memory_order_acquire)) {
+        SA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < SA_MAX_DEVICES) done[dev].store(true, std::memory_order_release);
+    }
     return SA_OK;
 }
 
@@ -583,11 +680,10 @@ static int launch_tile_variant(const TileArgs &a, cudaStream_t st) {
     const long long total = (long long)tiles_per_batch * a.nbatch;
     const long long grid = (total + P::TPC - 1) / P::TPC;
     const size_t smem = P::smem_bytes();
-    static bool attr_done = false;
-    if (smem > 48 * 1024 && !attr_done) {
-        SA_CUDA(cudaFuncSetAttribute(ntt_tile_kernel<LOGL, ELOG, C, FLAGS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+    if (smem > 48 * 1024) {
+        static std::atomic<bool> attr_done[SA_MAX_DEVICES];
+        const int rc = optin_smem(ntt_tile_kernel<LOGL, ELOG, C, FLAGS>, attr_done, smem);
+        if (rc != SA_OK) return rc;
     }
     ntt_tile_kernel<LOGL, ELOG, C, FLAGS><<<(unsigned)grid, P::THREADS, smem, st>>>(a, total, tiles_per_batch);
     SA_LAUNCH_CHECK();
@@ -665,7 +761,7 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
         if (out != in) SA_CUDA(cudaMemcpyAsync(out, in, 16 * batch, cudaMemcpyDeviceToDevice, st));
         return SA_OK;
     }
-    NttPlan *p = nullptr;
+    PlanPtr p;  // keeps the tables alive until the launches below are enqueued (cudaFree waits for them)
     int rc = get_plan(&p, log_n, fe_from_limbs(root), inverse, st);
     if (rc != SA_OK) return rc;
     TileArgs a;
@@ -790,8 +886,9 @@ int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t r
     std::vector<size_t> counts;
     {
         std::vector<size_t> head;
-        if (g_host_ramp)
-            for (size_t c = per_chunk >> g_host_ramp; c < per_chunk; c <<= 1) head.push_back(c ? c : 1);
+        // (per_chunk <= 1 has nothing to ramp; the start is clamped so that c <<= 1 always makes progress)
+        if (g_host_ramp && per_chunk > 1)
+            for (size_t c = std::max<size_t>(1, per_chunk >> g_host_ramp); c < per_chunk; c <<= 1) head.push_back(c);
         size_t ramp = 0;
         for (size_t c : head) ramp += c;
         if (2 * ramp >= batch) head.clear(), ramp = 0;
@@ -946,11 +1043,10 @@ int sa_zerofier(void *out, const void *domain, size_t k, void *stream) {
     if (k > (size_t)ZF_MAXK) return SA_ESIZE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(fe) * (2 * k + 1);
-    static bool attr_done = false;
-    if (!attr_done) {
-        SA_CUDA(cudaFuncSetAttribute(k_zerofier, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(fe) * (2 * ZF_MAXK + 1))));
-        attr_done = true;
+    {
+        static std::atomic<bool> attr_done[SA_MAX_DEVICES];
+        const int rc = optin_smem(k_zerofier, attr_done, sizeof(fe) * (2 * ZF_MAXK + 1));
+        if (rc != SA_OK) return rc;
     }
     k_zerofier<<<1, ZF_THREADS, smem, st>>>((fe *)out, (const fe *)domain, (int)k);
     SA_LAUNCH_CHECK();
@@ -1100,27 +1196,20 @@ int sa_gather(void *out, const void *values, size_t n, const uint64_t *indices_h
     return SA_OK;
 }
 
-// x_i^-1 tables: xinv[i] = omega^-i (Montgomery), i < n/2, cached per (device, omega, n)
-using XinvKey = std::tuple<int, uint64_t, uint64_t, uint64_t>;
-static std::map<XinvKey, fe *> g_xinv;
-static int get_xinv(fe **out, const fe &omega, size_t n, cudaStream_t st) {
+// x_i^-1 tables: xinv[i] = omega^-i (Montgomery), i < n/2, cached per (device, omega, n) in the LRU above
+static int get_xinv(XinvPtr *out, const fe &omega, size_t n, cudaStream_t st) {
     int dev = 0;
     SA_CUDA(cudaGetDevice(&dev));
-    const XinvKey key(dev, (uint64_t)omega.v[0] | ((uint64_t)omega.v[1] << 32),
-                      (uint64_t)omega.v[2] | ((uint64_t)omega.v[3] << 32), (uint64_t)n);
-    std::lock_guard<std::mutex> lock(g_plan_mu);
-    auto it = g_xinv.find(key);
-    if (it != g_xinv.end()) {
-        *out = it->second;
-        return SA_OK;
-    }
+    const CacheKey key(1, dev, (uint64_t)n, (uint64_t)omega.v[0] | ((uint64_t)omega.v[1] << 32),
+                       (uint64_t)omega.v[2] | ((uint64_t)omega.v[3] << 32), 0);
+    if ((*out = cache_find<XinvTable>(key))) return SA_OK;
     const fe winv_m = fe_mont_inv(fe_to_mont(omega));
-    fe *tab = nullptr;
-    int rc = build_pow_table(&tab, winv_m, fe_mont_one(), (long long)(n / 2), st);
+    XinvPtr made = std::make_shared<XinvTable>();
+    made->device = dev;
+    int rc = build_pow_table(*made, &made->tab, winv_m, fe_mont_one(), (long long)(n / 2), st);
     if (rc != SA_OK) return rc;
     SA_CUDA(cudaStreamSynchronize(st));  // complete before other streams can find it in the cache
-    g_xinv[key] = tab;
-    *out = tab;
+    *out = cache_publish<XinvTable>(key, made);
     return SA_OK;
 }
 
@@ -1136,13 +1225,13 @@ int sa_fri_fold(void *next, const void *cw, size_t n, const uint64_t alpha[2], c
                 const uint64_t omega[2], void *stream) {
     if (!host_is_pow2(n) || n < 2) return SA_ENOTPOW2;
     cudaStream_t st = (cudaStream_t)stream;
-    fe *xinv = nullptr;
+    XinvPtr xinv;
     int rc = get_xinv(&xinv, fe_from_limbs(omega), n, st);
     if (rc != SA_OK) return rc;
     fe s_m, inv2_m;
     fri_scalars(&s_m, &inv2_m, alpha, offset);
     k_fri_fold<<<grid_for((long long)(n / 2), 128), 128, 0, st>>>((fe *)next, (const fe *)cw,
-                                                                 (long long)(n / 2), xinv, s_m, inv2_m);
+                                                                 (long long)(n / 2), xinv->tab, s_m, inv2_m);
     SA_LAUNCH_CHECK();
     return SA_OK;
 }
@@ -1151,7 +1240,7 @@ int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const ui
                  const uint64_t offset[2], const uint64_t omega[2], void *stream) {
     if (!host_is_pow2(n) || n < 2) return SA_ENOTPOW2;
     cudaStream_t st = (cudaStream_t)stream;
-    fe *xinv = nullptr;
+    XinvPtr xinv;
     int rc = get_xinv(&xinv, fe_from_limbs(omega), n, st);
     if (rc != SA_OK) return rc;
     SA_CUDA(cudaMemsetAsync(next_tree, 0, 64, st));
@@ -1162,7 +1251,7 @@ int sa_fri_round(void *next, void *next_tree, const void *cw, size_t n, const ui
     a.mode = 2;
     a.prev = (const fe *)cw;
     a.next = (fe *)next;
-    a.xinv = xinv;
+    a.xinv = xinv->tab;
     fri_scalars(&a.s_m, &a.inv2_m, alpha, offset);
     return merkle_reduce(a, st);
 }
@@ -1243,7 +1332,7 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
         }
         if (!want) break;
         // fold layer r into layer r+1 and build its tree, one fused kernel (+ upper-level launches)
-        fe *xinv = nullptr;
+        XinvPtr xinv;
         if ((rc = get_xinv(&xinv, om, len, st)) != SA_OK) return rc;
         uint8_t *next_tree = tree + 128 * len;  // this tree has 2 * len nodes of 64 bytes
         MerkleArgs a;
@@ -1253,7 +1342,7 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
         a.mode = 2;
         a.prev = cur;
         a.next = layer_out;
-        a.xinv = xinv;
+        a.xinv = xinv->tab;
         a.inv2_m = inv2_m;
         a.s_m = fe_montmul(fe_montmul(fe_to_mont(fe_from_limbs(alpha)), inv2_m), oinv_m);  // alpha / (2 offset)
         if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
@@ -1266,6 +1355,34 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
         off = fe_montmul(off_m, off);   // offset^2
         oinv_m = fe_montmul(oinv_m, oinv_m);  // (offset^2)^-1, stays in Montgomery form
     }
+    return SA_OK;
+}
+
+size_t sa_cache_limit(size_t bytes) {
+    cache_config();
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    g_cache_limit = bytes;
+    cache_make_room(0);
+    return g_cache_bytes;
+}
+size_t sa_cache_bytes(void) {
+    std::lock_guard<std::mutex> lock(g_plan_mu);
+    return g_cache_bytes;
+}
+int sa_release_workspaces(void) {
+    SA_CUDA(cudaDeviceSynchronize());
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    for (auto it = g_ws.begin(); it != g_ws.end();) {
+        if (std::get<0>(it->first) == dev) {
+            if (it->second.first) cudaFree(it->second.first);
+            it = g_ws.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    cudaGetLastError();
     return SA_OK;
 }
 

@@ -85,6 +85,7 @@ static PyObject *sa_unpack_ints(PyObject *, PyObject *arg) {
             PyList_SET_ITEM(out, i, v);
         }
     }
+    if (gc_was_on) PyGC_Enable();
     PyBuffer_Release(&buf);
     return out;
 }

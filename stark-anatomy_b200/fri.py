@@ -38,6 +38,8 @@ from ntt import intt
 
 import sa_engine
 import sa_marshal
+import sa_devlist
+from sa_devlist import DeviceCodeword
 
 
 class Merkle(_HostMerkle):
@@ -59,6 +61,11 @@ class Merkle(_HostMerkle):
     _CACHE_LIMIT = 1 << 30
 
     def _device_tree(data_array):
+        if isinstance(data_array, DeviceCodeword):
+            # values already in HBM (what ntt / fast_coset_evaluate return): the tree is built once and
+            # stays attached to the object -- no pack, no upload, no fingerprint
+            n = len(data_array)
+            return data_array.device_tree() if n and not n & (n - 1) else None
         n = len(data_array)
         if n == 0 or n & (n - 1):
             return None
@@ -84,68 +91,20 @@ class Merkle(_HostMerkle):
     def commit(data_array):
         tree = Merkle._device_tree(data_array)
         if tree is None:
-            return _HostMerkle.commit(data_array)
+            return _HostMerkle.commit(list(data_array) if isinstance(data_array, DeviceCodeword) else data_array)
+        if isinstance(data_array, DeviceCodeword):
+            return data_array.root()
         return sa_engine.get_engine().tree_root(tree)
 
     def open(index, data_array):
+        if isinstance(data_array, DeviceCodeword) and len(data_array) >= 2 and Merkle._device_tree(data_array) is not None:
+            assert(0 <= index and index < len(data_array)), "cannot open invalid index"
+            return data_array.open_paths([index])[0]
         tree = Merkle._device_tree(data_array)
         if tree is None or len(data_array) < 2:
-            return _HostMerkle.open(index, data_array)
+            return _HostMerkle.open(index, list(data_array) if isinstance(data_array, DeviceCodeword) else data_array)
         assert(0 <= index and index < len(data_array)), "cannot open invalid index"
         return sa_engine.get_engine().merkle_open(tree, [index])[0]
-
-
-class DeviceCodeword:
-    """A FRI layer that lives on the GPU and behaves like the list the reference
-    returns from ``Fri.commit``: len(), indexing, iteration, ==.  Elements are
-    materialised on demand and cached, so repeated indexing returns the SAME
-    FieldElement object (a real list would, and pickle's memo sees the difference).
-    """
-
-    def __init__(self, vec, tree, field, length):
-        self._vec, self._tree, self._field, self._len = vec, tree, field, length
-        self._cache = {}
-        self._full = None
-
-    def __len__(self):
-        return self._len
-
-    def prefetch(self, indices):
-        missing = [i for i in dict.fromkeys(indices) if i not in self._cache]
-        if self._full is not None or not missing:
-            return
-        raw = sa_engine.get_engine().gather(self._vec, missing)
-        for i, el in zip(missing, sa_marshal.unpack(raw, self._field, FieldElement)):
-            self._cache[i] = el
-
-    def tolist(self):
-        if self._full is None:
-            full = sa_marshal.unpack(sa_engine.get_engine().download(self._vec), self._field, FieldElement)
-            for i, el in self._cache.items():  # keep identities handed out earlier
-                full[i] = el
-            self._full = full
-        return self._full
-
-    def __getitem__(self, i):
-        if isinstance(i, slice):
-            return self.tolist()[i]
-        if i < 0:
-            i += self._len
-        if not 0 <= i < self._len:
-            raise IndexError("list index out of range")
-        if self._full is not None:
-            return self._full[i]
-        if i not in self._cache:
-            self.prefetch([i])
-        return self._cache[i]
-
-    def __iter__(self):
-        return iter(self.tolist())
-
-    def __eq__(self, other):
-        return self.tolist() == (other.tolist() if isinstance(other, DeviceCodeword) else other)
-
-    __hash__ = None
 
 
 class Fri:
@@ -212,11 +171,15 @@ class Fri:
 
         # the whole ladder runs on the device: round 0 = leaf hashing + tree, every later round =
         # one fused kernel (split-and-fold fri.py:85 + leaf hashing + tree); only the 64-byte roots
-        # come back, through on_root
-        vecs, trees = eng.fri_commit(eng.upload(sa_marshal.pack(codeword)), rounds, offset, omega, on_root)
+        # come back, through on_root.  A DeviceCodeword (what fast_coset_evaluate returns) is already
+        # in HBM: no pack, no upload.
+        vecs, trees = eng.fri_commit(sa_devlist.to_device(codeword), rounds, offset, omega, on_root)
 
         codewords = [codeword]
-        self._resident[id(codeword)] = (codeword, vecs[0], trees[0])
+        if isinstance(codeword, DeviceCodeword):
+            codeword.attach_tree(trees[0])
+        else:
+            self._resident[id(codeword)] = (codeword, vecs[0], trees[0])
         for r in range(1, rounds):
             codewords.append(DeviceCodeword(vecs[r], trees[r], self.field, N >> r))
         # send last codeword (a real list: it is pickled into the transcript)
@@ -229,14 +192,23 @@ class Fri:
         return codewords
 
     # ---------------------------------------------------------------- query --
-    def _device_layer(self, layer):
-        """(vector, tree) of a layer: resident from commit, else uploaded and hashed now"""
+    def _device_layer(self, layer, check=None):
+        """(vector, tree) of a layer: resident from commit, else uploaded and hashed now.
+        check = (indices, elements the caller is about to reveal from a plain list): the reference
+        re-hashes the list it is given on every Merkle.open (merkle.py:26-27), so a list that was
+        modified in place after commit must not be answered from the tree of its old contents; the
+        revealed positions are compared with the resident vector and a mismatch drops the cache."""
         if isinstance(layer, DeviceCodeword):
-            return layer._vec, layer._tree
-        hit = self._resident.get(id(layer))
-        if hit is not None and hit[0] is layer:
-            return hit[1], hit[2]
+            return layer.device_vector(), layer.device_tree()
         eng = sa_engine.get_engine()
+        hit = self._resident.get(id(layer))
+        if hit is not None and hit[0] is layer and eng.length(hit[1]) == len(layer):
+            fresh = True
+            if check is not None and len(check[0]):
+                resident = bytes(memoryview(eng.gather(hit[1], list(check[0]))).cast("B"))
+                fresh = resident == bytes(sa_marshal.pack(check[1]))
+            if fresh:
+                return hit[1], hit[2]
         vec = eng.upload(sa_marshal.pack(layer))
         tree = eng.merkle_tree(vec)
         self._resident[id(layer)] = (layer, vec, tree)
@@ -248,21 +220,29 @@ class Fri:
         a_indices = [index for index in c_indices]
         b_indices = [index + len(current_codeword) // 2 for index in c_indices]
         s_range = range(self.num_colinearity_tests)
+        ab = [a_indices[s] for s in s_range] + [b_indices[s] for s in s_range]
+        cc = [c_indices[s] for s in s_range]
 
         if isinstance(current_codeword, DeviceCodeword):
-            current_codeword.prefetch([a_indices[s] for s in s_range] + [b_indices[s] for s in s_range])
+            current_codeword.prefetch(ab)
         if isinstance(next_codeword, DeviceCodeword):
-            next_codeword.prefetch([c_indices[s] for s in s_range])
+            next_codeword.prefetch(cc)
 
         # reveal leafs
         for s in s_range:
             proof_stream.push((current_codeword[a_indices[s]], current_codeword[b_indices[s]], next_codeword[c_indices[s]]))
 
         # reveal authentication paths: one gather per layer from the resident trees
-        _, cur_tree = self._device_layer(current_codeword)
-        _, nxt_tree = self._device_layer(next_codeword)
-        cur_paths = eng.merkle_open(cur_tree, [a_indices[s] for s in s_range] + [b_indices[s] for s in s_range])
-        nxt_paths = eng.merkle_open(nxt_tree, [c_indices[s] for s in s_range])
+        if isinstance(current_codeword, DeviceCodeword):
+            cur_paths = current_codeword.open_paths(ab)
+        else:
+            _, cur_tree = self._device_layer(current_codeword, (ab, [current_codeword[i] for i in ab]))
+            cur_paths = eng.merkle_open(cur_tree, ab)
+        if isinstance(next_codeword, DeviceCodeword):
+            nxt_paths = next_codeword.open_paths(cc)
+        else:
+            _, nxt_tree = self._device_layer(next_codeword, (cc, [next_codeword[i] for i in cc]))
+            nxt_paths = eng.merkle_open(nxt_tree, cc)
         k = self.num_colinearity_tests
         for s in s_range:
             proof_stream.push(cur_paths[s])
@@ -307,7 +287,7 @@ class Fri:
 
         # extract last codeword and check it against the last root
         last_codeword = proof_stream.pull()
-        last_vec = eng.upload(sa_marshal.pack(last_codeword))
+        last_vec = sa_devlist.to_device(last_codeword)
         if roots[-1] != eng.tree_root(eng.merkle_tree(last_vec)):
             print("last codeword is not well formed")
             return False

@@ -19,6 +19,7 @@ from algebra import FieldElement
 
 import sa_engine
 import sa_marshal
+import sa_devlist
 import sa_accel  # noqa: F401  (opt-in Polynomial.__mul__ acceleration; inert unless enabled)
 
 _P = sa_engine.P
@@ -60,26 +61,30 @@ def _upload_padded(elements, total):
 
 
 # --------------------------------------------------------------------- ntt --
+# ntt / intt / fast_coset_evaluate return a sa_devlist.DeviceCodeword: a list-like whose values stay in
+# HBM (len, indexing, iteration, ==, slicing, + ... work; elements are created when read).  Handing it
+# back to ntt / intt / Merkle.commit / Merkle.open / Fri.commit / Fri.prove costs no pack and no upload
+# (SURVEY 8 f3); SA_B200_DEVICE_LISTS=0 returns plain lists instead.
 def ntt(primitive_root, values):
     assert(len(values) & (len(values) - 1) == 0), "cannot compute ntt of non-power-of-two sequence"
     if len(values) <= 1:
         return values
-    field = values[0].field
+    field = sa_devlist.field_of(values)
     _check_field(field)
     eng = _engine()
-    out = eng.ntt(eng.upload(sa_marshal.pack(values)), _log2(len(values)), primitive_root.value)
-    return _unpack(out, field)
+    out = eng.ntt(sa_devlist.to_device(values), _log2(len(values)), primitive_root.value)
+    return sa_devlist.wrap(out, field)
 
 
 def intt(primitive_root, values):
     assert(len(values) & (len(values) - 1) == 0), "cannot compute intt of non-power-of-two sequence"
     if len(values) == 1:
         return values
-    field = values[0].field
+    field = sa_devlist.field_of(values)
     _check_field(field)
     eng = _engine()
-    out = eng.ntt(eng.upload(sa_marshal.pack(values)), _log2(len(values)), primitive_root.value, inverse=True)
-    return _unpack(out, field)
+    out = eng.ntt(sa_devlist.to_device(values), _log2(len(values)), primitive_root.value, inverse=True)
+    return sa_devlist.wrap(out, field)
 
 
 def _shrink(root, order, degree, p):
@@ -199,7 +204,7 @@ def fast_coset_evaluate(polynomial, offset, generator, order):
         return polynomial.scale(offset).coefficients + [field.zero()] * (order - ncoef)
     coeffs = eng.upload(sa_marshal.pack(polynomial.coefficients))
     scaled = eng.pad(eng.scale(coeffs, offset.value), total) if ncoef else eng.zeros(total)
-    return _unpack(eng.ntt(scaled, _log2(total), generator.value), field)
+    return sa_devlist.wrap(eng.ntt(scaled, _log2(total), generator.value), field)
 
 
 def fast_coset_divide(lhs, rhs, offset, primitive_root, root_order):  # clean division only!

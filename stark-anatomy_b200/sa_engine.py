@@ -51,6 +51,9 @@ SYMBOLS = [
     ("sa_fri_fold", _ci, [_vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
     ("sa_fri_round", _ci, [_vp, _vp, _vp, _sz, _u64p, _u64p, _u64p, _vp]),
     ("sa_fri_commit", _ci, [_vp, _vp, _vp, _sz, _ci, _u64p, _u64p, _vp, _vp, _vp]),
+    ("sa_cache_limit", _sz, [_sz]),
+    ("sa_cache_bytes", _sz, []),
+    ("sa_release_workspaces", _ci, []),
     ("sa_selftest_field", ctypes.c_longlong, [_sz, ctypes.c_uint64]),
     ("sa_microbench", ctypes.c_double, [_ci, _ci, _ci, _ci, _ci]),
 ]
@@ -91,6 +94,13 @@ class CudaEngine:
         self.torch = torch
         self.lib = load_library()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        # host<->device traffic this engine object has caused (calls and bytes); tools/config5.py and the
+        # tests use it to show which boundary crossings are left
+        self.stats = {"h2d_calls": 0, "h2d_bytes": 0, "d2h_calls": 0, "d2h_bytes": 0}
+
+    def _count(self, kind, nbytes):
+        self.stats[kind + "_calls"] += 1
+        self.stats[kind + "_bytes"] += int(nbytes)
 
     # ------------------------------------------------------------ plumbing
     def _stream(self):
@@ -118,14 +128,18 @@ class CudaEngine:
         """packed 16-byte elements (bytearray / numpy / pinned tensor) -> device vector"""
         torch = self.torch
         if isinstance(buf, torch.Tensor):
+            if not buf.is_cuda:
+                self._count("h2d", buf.numel() * buf.element_size())
             return buf.reshape(-1, 2).to(self.device, non_blocking=True)
         if len(buf) == 0:
             return self.empty(0)
         host = torch.frombuffer(buf, dtype=torch.int64).reshape(-1, 2)
+        self._count("h2d", host.numel() * 8)
         return host.to(self.device)
 
     def download(self, vec):
         """device vector -> numpy uint64[n, 2] (buffer protocol, 16 bytes/element)"""
+        self._count("d2h", vec.numel() * 8)
         return vec.contiguous().cpu().numpy()
 
     def pad(self, vec, n):
@@ -202,7 +216,14 @@ class CudaEngine:
         return tree
 
     def tree_root(self, tree):
+        self._count("d2h", 64)
         return bytes(tree[1].cpu().numpy().tobytes())
+
+    def download_tree(self, tree):
+        """the whole heap-ordered tree as a host array uint8[2n, 64] (small trees: paths are then read on
+        the host, O(log n) per opened index and no device round trip)"""
+        self._count("d2h", tree.numel())
+        return tree.cpu().numpy()
 
     def merkle_open(self, tree, indices):
         """authentication paths (lists of 64-byte digests, bottom-up) for leaf indices"""
@@ -222,6 +243,8 @@ class CudaEngine:
         out = self.torch.empty((k, depth, 64), dtype=self.torch.uint8, device=self.device)
         idx = (ctypes.c_uint64 * k)(*indices)
         self._check(self.lib.sa_merkle_open(out.data_ptr(), tree.data_ptr(), n, idx, k, self._stream()))
+        self._count("h2d", 8 * k)
+        self._count("d2h", k * depth * 64)
         raw = out.cpu().numpy().tobytes()
         return [[raw[(q * depth + l) * 64:(q * depth + l + 1) * 64] for l in range(depth)] for q in range(k)]
 
@@ -233,6 +256,8 @@ class CudaEngine:
         if k:
             idx = (ctypes.c_uint64 * k)(*indices)
             self._check(self.lib.sa_gather(out.data_ptr(), vec.data_ptr(), vec.shape[0], idx, k, self._stream()))
+            self._count("h2d", 8 * k)
+            self._count("d2h", 16 * k)
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------ fri

@@ -32,6 +32,22 @@ def pytest_sessionstart(session):
         print("conftest: native build step failed: %r" % (exc,))
 
 
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device skips the gpu-marked tests instead of erroring
+    on the engine fixture (the product itself still fails loudly without CUDA: that is a test of its own)."""
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible (gpu tests run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)

@@ -175,14 +175,24 @@ def case_fri_commit(max_n):
 
 
 def case_fri_commit_2_20():
-    c = [c for c in load_golden("fri.json")["commit"] if c["n"] == 1 << 20][0]
+    """BASELINE config 4: all 12 full 64-byte roots, the last codeword and the pickled transcript of the
+    reference's own Fri.commit on the seed-1 2^20 codeword (tests/golden/fri_2_20.json)"""
+    c = load_golden("fri_2_20.json")
     n = 1 << 20
     cw = seeded(1, n)
     fri = F.Fri(T.field.generator(), T.field.primitive_nth_root(n), n, 4, 64)
     ps = F.ProofStream()
-    fri.commit(cw, ps)
+    layers = fri.commit(cw, ps)
     roots = [o for o in ps.objects if isinstance(o, bytes)]
-    assert [r[:8].hex() for r in roots] == c["roots8"]
+    assert [r.hex() for r in roots] == c["roots"]
+    assert len(ps.objects[-1]) == c["last_len"] and digest(ps.objects[-1]) == c["last_codeword_digest"]
+    assert hashlib.sha256(pickle.dumps(ps.objects)).hexdigest() == c["transcript_sha256"]
+    assert [len(l) for l in layers] == [n >> r for r in range(12)]
+    # the same ladder from a device-resident codeword (what fast_coset_evaluate hands to Fri.prove)
+    dev = F.DeviceCodeword(N._engine().upload(__import__("sa_marshal").pack(cw)), None, T.field)
+    ps2 = F.ProofStream()
+    fri.commit(dev, ps2)
+    assert pickle.dumps(ps2.objects) == pickle.dumps(ps.objects)
 
 
 def case_fri_prove(max_n, with_verify=True):
@@ -288,6 +298,78 @@ def case_merkle_class():
     root = F.Merkle.commit(data)
     for i in range(16):
         assert F.Merkle.verify(root, i, F.Merkle.open(i, data), data[i])
+
+
+# ----------------------------------------------------- device-resident lists
+def case_device_list():
+    """sa_devlist.DeviceCodeword: the list-like ntt / intt / fast_coset_evaluate return (section 8 f3)"""
+    import sa_devlist
+    import sa_engine
+    n = 256
+    w = T.field.primitive_nth_root(n)
+    xs = seeded(31, n)
+    out = N.ntt(w, xs)
+    assert isinstance(out, sa_devlist.DeviceCodeword) and not isinstance(out, list)
+    ref = load_golden  # noqa: F841
+    plain = list(out)
+    assert len(out) == n and vals(plain) == vals(N.ntt(w, list(xs)))
+    # list protocol
+    assert out[3] is out[3] and out[-1] is out[n - 1] and out[3].value == plain[3].value
+    assert all(type(o) is T.FieldElement and o.field is T.field for o in out)
+    assert out == plain and plain == out and not (out != plain) and out != plain[:-1]
+    assert vals(out[10:20]) == vals(plain[10:20]) and type(out[10:20]) is list
+    assert vals(out + [T.fe(1)]) == vals(plain) + [1] and vals([T.fe(1)] + out) == [1] + vals(plain)
+    assert plain[5] in out and out.index(plain[5]) == 5 and out.count(plain[5]) == 1
+    assert vals(reversed(out)) == vals(plain)[::-1]
+    with pytest.raises(IndexError):
+        out[n]
+    assert pickle.loads(pickle.dumps(out)) == plain
+    # the chain stays on the device: intt(ntt(x)) == x, no element is created in between
+    eng = sa_engine.get_engine()
+    back = N.intt(w, N.ntt(w, xs))
+    assert vals(back) == vals(xs)
+    # a big one is read through gathers, identity per index is stable, tolist keeps identities
+    big_n = 1 << 15
+    big = N.ntt(T.field.primitive_nth_root(big_n), seeded(32, big_n))
+    a, b = big[12345], big[7]
+    assert big[12345] is a and big._full is None
+    full = big.tolist()
+    assert full[12345] is a and full[7] is b and big[100] is full[100]
+    # Merkle on a device list == the host class on the plain list; opens come from the attached tree
+    host = F._HostMerkle
+    assert F.Merkle.commit(out) == host.commit(plain)
+    for i in (0, 1, 77, n - 1):
+        assert F.Merkle.open(i, out) == host.open(i, plain)
+        assert F.Merkle.verify(F.Merkle.commit(out), i, F.Merkle.open(i, out), out[i])
+    with pytest.raises(AssertionError, match="cannot open invalid index"):
+        F.Merkle.open(n, out)
+    big_tree = F.Merkle.commit(big)
+    assert big_tree == host.commit(full) and F.Merkle.open(4242, big) == host.open(4242, full)
+    # mutation: the host list becomes the truth, the device copy and tree are rebuilt on demand
+    out[0] = T.fe(123)
+    plain[0] = T.fe(123)
+    assert out == plain and len(out) == n
+    assert F.Merkle.commit(out) == host.commit(plain) and F.Merkle.open(0, out) == host.open(0, plain)
+    assert vals(N.intt(w, out)) == vals(N.intt(w, plain))
+    out.append(T.fe(5))
+    assert len(out) == n + 1 and out[-1].value == 5
+    # a plain list modified in place after Fri.commit is re-hashed by query, like merkle.py:26-27
+    m = 64
+    cw = seeded(33, m)
+    fri = F.Fri(T.field.generator(), T.field.primitive_nth_root(m), m, 2, 4)
+    ps = F.ProofStream()
+    layers = fri.commit(cw, ps)
+    idx = [1, 5, 9, 13]
+    cw[1] = T.fe(999)
+    qs = F.ProofStream()
+    fri.query(layers[0], layers[1], idx, qs)
+    assert qs.objects[4] == host.open(1, cw)
+    # SA_B200_DEVICE_LISTS=0 behaviour: plain lists
+    sa_devlist.ENABLED = False
+    try:
+        assert type(N.ntt(w, xs)) is list
+    finally:
+        sa_devlist.ENABLED = True
 
 
 # ----------------------------------------------------------------- sa_accel

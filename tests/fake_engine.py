@@ -32,11 +32,13 @@ class OracleEngine:
         return vec.shape[0]
 
     def upload(self, buf):
+        self._log("upload", len(buf) // 16 if not isinstance(buf, np.ndarray) else buf.size // 2)
         if isinstance(buf, np.ndarray):
             return buf.reshape(-1, 2).astype(np.uint64)
         return np.frombuffer(bytes(buf), dtype="<u8").reshape(-1, 2).copy()
 
     def download(self, vec):
+        self._log("download", vec.shape[0])
         return np.ascontiguousarray(vec)
 
     def pad(self, vec, n):
@@ -99,6 +101,10 @@ class OracleEngine:
 
     def tree_root(self, tree):
         return tree[1].tobytes()
+
+    def download_tree(self, tree):
+        self._log("download_tree", tree.shape[0] // 2)
+        return np.ascontiguousarray(tree)
 
     def merkle_open(self, tree, indices):
         self._log("merkle_open", len(indices))

@@ -384,6 +384,52 @@ def gen_faststark_trace():
         os.urandom = real_urandom
 
 
+# ---------------------------------- full 64-byte roots of the 2^20 FRI ladder (BASELINE config 4)
+def gen_fri_2_20():
+    """Fri.commit of the reference on the seed-1 2^20 codeword (ef 4, 64 tests, 12 rounds): every
+    round's full Merkle root and the digest of the last codeword.  ~75 s of reference time."""
+    n = 1 << 20
+    rng = random.Random(1)
+    cw = [fe(rng.randrange(P)) for _ in range(n)]
+    f = Fri(field.generator(), field.primitive_nth_root(n), n, 4, 64)
+    ps = ProofStream()
+    layers = f.commit(cw, ps)
+    roots = [o.hex() for o in ps.objects if isinstance(o, bytes)]
+    assert len(roots) == 12 and len(layers) == 12
+    dump("fri_2_20.json", {"seed": 1, "n": n, "ef": 4, "tests": 64, "rounds": 12, "roots": roots,
+                           "last_codeword_digest": vector_digest(ps.objects[-1]), "last_len": len(ps.objects[-1]),
+                           "transcript_sha256": hashlib.sha256(pickle.dumps(ps.objects)).hexdigest()})
+
+
+# ------------------------------------------ FastRPSSS keygen / sign (BASELINE config 5 parameters)
+def gen_rpsss():
+    """One seeded keygen + sign of the UNMODIFIED fast_rpsss.py (expansion 4, 64 colinearity checks,
+    security level 128; FRI domain 4096, 4 rounds).  ~40 s of reference time; the 200 s reference
+    verification is not run here (the signature is checked by the verifier in the GPU test)."""
+    import time
+    import fast_rpsss
+    rng = random.Random(700)
+    real_urandom = os.urandom
+    os.urandom = lambda n: bytes(rng.getrandbits(8) for _ in range(n))
+    try:
+        t0 = time.perf_counter()
+        r = fast_rpsss.FastRPSSS()
+        t_init = time.perf_counter() - t0
+        sk, pk = r.keygen()
+        doc = b"Hello, World!"
+        t0 = time.perf_counter()
+        sig = r.sign(sk, doc)
+        t_sign = time.perf_counter() - t0
+        dump("rpsss.json", {"urandom_seed": 700, "document": doc.hex(), "sk": str(sk.value), "pk": str(pk.value),
+                            "signature_sha256": hashlib.sha256(sig).hexdigest(), "signature_len": len(sig),
+                            "fri_domain_length": r.stark.fri_domain_length,
+                            "omicron_domain_length": r.stark.omicron_domain_length,
+                            "reference_seconds": {"init_preprocess": round(t_init, 2), "sign": round(t_sign, 2),
+                                                  "where": "dev container, 1 Xeon core, CPython 3.12"}})
+    finally:
+        os.urandom = real_urandom
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["field", "ntt", "poly", "merkle", "fri", "faststark"]
     if "field" in which:
@@ -398,3 +444,7 @@ if __name__ == "__main__":
         gen_fri()
     if "faststark" in which:
         gen_faststark_trace()
+    if "fri20" in which:      # not in the default set: ~75 s
+        gen_fri_2_20()
+    if "rpsss" in which:      # not in the default set: ~40 s
+        gen_rpsss()

@@ -12,7 +12,20 @@ import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "stark-anatomy_b200")
-REFERENCE = os.environ.get("STARK_REFERENCE", "/root/reference/code")
+
+
+
+def _find_reference():
+    """the reference's flat module directory: the read-only checkout in the dev container, else the copy
+    staged by __graft_entry__.stage_reference() under the git-ignored baseline/_ref/ (which travels to the
+    GPU box with the gpurun snapshot)"""
+    for cand in (os.environ.get("STARK_REFERENCE"), "/root/reference/code", os.path.join(ROOT, "baseline", "_ref", "code")):
+        if cand and os.path.isdir(cand):
+            return cand
+    return "/root/reference/code"
+
+
+REFERENCE = _find_reference()
 
 
 def setup_paths(use_reference=True):

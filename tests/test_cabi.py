@@ -51,7 +51,18 @@ def test_marshal_roundtrip_and_pickle_identity():
     xs = [T.fe(rng.randrange(T.field.p)) for _ in range(1000)] + [T.fe(0), T.fe(T.field.p - 1)]
     buf = sa_marshal.pack(xs)
     assert isinstance(buf, bytearray) and len(buf) == 16 * len(xs)
+    import gc
+    assert gc.isenabled()
     assert sa_marshal.unpack_ints(buf) == [x.value for x in xs]
+    assert gc.isenabled(), "unpack_ints must leave the cyclic collector as it found it"
+    sa_marshal.unpack(buf, xs[0].field, type(xs[0]))
+    assert gc.isenabled(), "unpack must leave the cyclic collector as it found it"
+    gc.disable()
+    try:  # and a collector the caller had switched off stays off
+        sa_marshal.unpack_ints(buf)
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
     ys = sa_marshal.unpack(buf, T.field, T.FieldElement)
     assert all(type(y) is T.FieldElement and y.field is T.field for y in ys)
     assert pickle.dumps(ys) == pickle.dumps(xs)

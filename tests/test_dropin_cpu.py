@@ -72,6 +72,10 @@ def test_accel_polymul():
     C.case_accel_polymul()
 
 
+def test_device_list():
+    C.case_device_list()
+
+
 def test_reference_style_properties():
     C.case_reference_style_properties()
 

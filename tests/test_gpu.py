@@ -3,6 +3,7 @@ C ABI (include/sa_b200.h) via sa_engine's ctypes binding and is compared bit-exa
 the CPU oracle on the same seeded inputs, with the reference's golden digests, or through
 size-independent properties at BASELINE.json's full sizes."""
 import ctypes
+import os
 import random
 
 import numpy as np
@@ -14,6 +15,7 @@ import sa_engine
 
 pytestmark = pytest.mark.gpu
 P = O.P
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -180,7 +182,7 @@ def test_ntt_in_place_and_host_entry(eng):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("log_n,batch", [(16, 70), (18, 9), (12, 3)])
+@pytest.mark.parametrize("log_n,batch", [(16, 70), (18, 9), (12, 3), (21, 3), (22, 2)])
 def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
     """sa_ntt_host cuts a batch into ramped chunks over several copy streams (32 MiB chunks, first and
     last halved): ragged batch sizes, chunk boundaries and the single-chunk path against the oracle"""
@@ -207,6 +209,67 @@ def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
         del hx, hy
     finally:
         assert eng.lib.sa_host_free(p_in) == 0 and eng.lib.sa_host_free(p_out) == 0
+
+
+@pytest.mark.parametrize("env", [{"SA_HOST_RAMP": "2"}, {"SA_HOST_CHUNK_MIB": "16"},
+                                 {"SA_HOST_RAMP": "3", "SA_HOST_CHUNK_MIB": "64", "SA_HOST_STREAMS": "2"}])
+def test_ntt_host_entry_pipeline_settings(eng, env):
+    """the pipeline knobs are read once per process, so every setting runs in its own interpreter: chunk
+    sizes whose ramp start rounds to zero transforms (round 1: an endless loop) and transforms
+    larger than a chunk must all give the oracle's result"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, ctypes, numpy as np
+sys.path[:0] = [%r, %r]
+import sa_engine, oracle as O
+eng = sa_engine.get_engine()
+for log_n, batch in ((20, 5), (21, 2), (16, 33)):
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    rng = np.random.default_rng(log_n)
+    x = np.stack([rng.integers(0, 1 << 64, size=n * batch, dtype=np.uint64),
+                  rng.integers(0, 0xCB80000000000000, size=n * batch, dtype=np.uint64)], axis=1)
+    out = np.zeros_like(x)
+    rc = eng.lib.sa_ntt_host(out.ctypes.data, x.ctypes.data, log_n, sa_engine._limbs(w), 0, batch, None)
+    assert rc == 0, rc
+    assert (out == O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2)).all(), (log_n, batch)
+print("PIPELINE_OK")
+''' % (os.path.join(ROOT_DIR, "stark-anatomy_b200"), os.path.join(ROOT_DIR, "oracle"))
+    out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=600,
+                         env=dict(os.environ, **env))
+    assert "PIPELINE_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
+
+
+def test_table_cache_is_bounded(eng):
+    """1000 distinct roots (fast_multiply's order shrinking makes new ones all the time) must not grow
+    HBM without bound: the plan / x^-1 table cache is an LRU bounded by sa_cache_limit"""
+    import torch
+    lib = eng.lib
+    log_n, n = 12, 1 << 12
+    base = O.primitive_nth_root(n)
+    x = up(eng, rand_np(5, n))
+    want0 = O.ntt_np(base, down(eng, x))
+    limit = 4 << 20
+    lib.sa_cache_limit(limit)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    try:
+        for k in range(1000):
+            root = pow(base, 2 * k + 1, P)  # odd powers: 1000 distinct primitive n-th roots
+            out = eng.ntt(x, log_n, root)
+            assert lib.sa_cache_bytes() <= limit
+            if k % 250 == 0:
+                assert (down(eng, out) == O.ntt_np(root, down(eng, x))).all()
+        torch.cuda.synchronize()
+        assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20  # (1000 plans would be ~100 MiB)
+        assert (down(eng, eng.ntt(x, log_n, base)) == want0).all()  # an evicted plan is simply rebuilt
+        assert lib.sa_cache_limit(0) == 0 and lib.sa_cache_bytes() == 0
+    finally:
+        lib.sa_cache_limit(4 << 30)
+    assert lib.sa_release_workspaces() == 0
+    assert (down(eng, eng.ntt(x, log_n, base)) == want0).all()
 
 
 def test_ntt_host_entry_from_two_threads(eng):
@@ -521,6 +584,41 @@ def test_dropin_merkle_class(eng):
 
 def test_dropin_accel_polymul(eng):
     C.case_accel_polymul()
+
+
+def test_dropin_device_list(eng):
+    C.case_device_list()
+
+
+def test_config5_unmodified_faststark_and_rpsss_on_the_cuda_engine(eng):
+    """BASELINE config 5 on the real engine: the reference's fast_stark.py / fast_rpsss.py, unmodified (staged
+    under baseline/_ref/code by __graft_entry__.stage_reference; /root/reference does not exist on the GPU
+    box), on top of the drop-in.  The seeded proof and the seeded signature must be the bytes the pure
+    reference produced (tests/golden/faststark_trace.json, rpsss.json) and must verify; between
+    fast_coset_evaluate and Fri.prove no 2^k-element list may cross the PCIe link (section 8 f3)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "config5.py")
+    out = subprocess.run([sys.executable, tool], text=True, capture_output=True, timeout=1500)
+    res = json.loads(out.stdout[out.stdout.index("{"):]) if "{" in out.stdout else {}
+    if res.get("unavailable"):
+        pytest.skip(res["unavailable"])
+    fs = res["faststark"]
+    assert "error" not in fs, fs
+    assert fs["byte_identical"] and fs["verify"] is True, fs
+    for key in ("rpsss", "rpsss_accel"):
+        r = res[key]
+        assert "error" not in r, r
+        assert r["byte_identical"], (key, r["signature_sha256"], r["golden_signature_sha256"])
+        assert r["verify"] is True and r["verify_second"] is True and r["verify_other_document"] is False
+        # what crossed the link during one sign: coefficient lists going up (each <= 1024 elements, far
+        # fewer bytes than ONE 4096-element codeword per commitment would be), small trees / vectors coming down
+        st = r["engine_during_sign"]
+        assert st["h2d_bytes"] < 8 * 4096 * 16, st
+    assert res["rpsss_accel"]["seconds"]["sign_warm"] < res["rpsss_accel"]["reference_seconds"]["sign"]
 
 
 def test_dropin_reference_style_properties(eng):
