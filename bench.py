@@ -34,7 +34,18 @@ BATCH = 16
 BUTTERFLIES_PER_NTT = (N // 2) * LOG_N  # 10 485 760
 METRIC = "128-bit field butterflies/sec on 2^20 NTT"
 UNIT = "butterflies/s"
+FRI_ROUNDS = 12                 # Fri(ef 4, 64 colinearity tests).num_rounds() at 2^20 (fri.py:22-28)
+FRI_COMPRESSIONS = 4193268      # leaves + inner nodes of the 12 trees
+FRI_ALG_BYTES = 50315264        # sum_r 16 N_r read + 8 N_r folded written
 WORKLOAD = "batch of %d independent 2^20-point forward NTTs over p=1+407*2^119 (configs[1] size, batched)" % BATCH
+
+
+def config_dict(world):
+    """the workload description both arms print (identical keys and values, so the driver's same_config
+    comparison holds); "parallelism" describes how the job is cut across the N GPUs of the launch"""
+    return {"workload": WORKLOAD, "log_n": LOG_N, "batch_per_gpu": BATCH,
+            "l2": "inputs larger than L2: %d MiB in + %d MiB out per step" % (BATCH * 16, BATCH * 16),
+            "parallelism": "batch sharded across %d GPU(s), no collective in the timed region" % world}
 
 
 def measured_peaks():
@@ -104,6 +115,23 @@ def cpu_arm(steps, warmup, batch):
     return batch * BUTTERFLIES_PER_NTT / dt, threads, dt
 
 
+def cpu_fri_commit(reps=2):
+    """the CPU oracle port of Fri.commit (fri.py:56-96) on the seed-1 2^20 codeword, all host threads;
+    returns (ms per commit, roots)"""
+    import numpy as np
+    import oracle as O
+    rng = np.random.default_rng(1)
+    cw = np.stack([rng.integers(0, 1 << 64, size=N, dtype=np.uint64),
+                   rng.integers(0, 0xCB80000000000000, size=N, dtype=np.uint64)], axis=1)
+    O.lib().so_set_threads(os.cpu_count() or 1)
+    w = O.primitive_nth_root(N)
+    O.fri_commit_np(cw, O.GENERATOR, w, 4, 64)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        roots, _, _ = O.fri_commit_np(cw, O.GENERATOR, w, 4, 64)
+    return (time.perf_counter() - t0) / reps * 1e3, roots
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -111,16 +139,25 @@ def run_reference(args):
     import __graft_entry__ as G
     G.build_oracle()
     value, threads, dt = cpu_arm(args.steps, args.warmup, BATCH)
+    fri_ms, _ = cpu_fri_commit()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u128 mod p (CPU unsigned __int128)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "log_n": LOG_N, "batch": BATCH},
+        "config": config_dict(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d steps of %d x 2^20-point ntt, oracle/stark_oracle.c so_ntt_batch (OpenMP, one "
-                                   "transform per thread); the reference itself is single-threaded pure Python "
-                                   "(5.5e4 butterflies/s, BASELINE.md section 2)" % (args.steps, BATCH)},
+                         "sample": "%d steps of %d x 2^20-point ntt, oracle/stark_oracle.c so_ntt_batch: OpenMP tasks, "
+                                   "every transform AND the recursion / combine loops inside it are tasks, so all "
+                                   "%d threads work although the batch is %d; the reference itself is single-threaded "
+                                   "pure Python (5.5e4 butterflies/s, 6 700x slower than this port, BASELINE.md section 2)"
+                                   % (args.steps, BATCH, threads, BATCH)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # second half of BASELINE.json's metric, same arm: Fri.commit of a 2^20 codeword (12 rounds,
+        # 4 193 268 blake2b compressions) on the CPU port, all threads
+        "fri_commit_ms_2_20": fri_ms,
+        "fri_commit": {"ms": fri_ms, "cores": threads, "kind": "port", "compressions_per_s": FRI_COMPRESSIONS / (fri_ms * 1e-3),
+                       "sample": "2 commits, oracle so_merkle_tree / so_fri_fold (OpenMP); the reference's own "
+                                 "Fri.commit takes 73 100 ms on one core (BASELINE.md section 2)"},
     }
     print(json.dumps(line))
 
@@ -256,53 +293,85 @@ def run_ours(args):
 
     # ---- FRI commit ms @ 2^20 (second half of BASELINE.json's metric), rank 0 only, list API excluded:
     #      device-resident codeword, 12 fused rounds, host Fiat-Shamir on the 64-byte roots
-    fri_ms = fri_cpu_ms = None
+    fri_ms = fri_cpu_ms = fri_const_ms = b2_peak = None
     if rank == 0:
         import hashlib
         import pickle
         cw = x[:N]
         omega0, off0 = w, O.GENERATOR
         rounds = O.fri_num_rounds(N, 4, 64)
+        assert rounds == FRI_ROUNDS
 
-        def fri_commit():
+        def fri_commit(constant=False):
             objs = []
 
             def on_root(r, root, want_alpha):  # the host side of fri.py:71-79 on a plain ProofStream
                 objs.append(root)
-                return O.sample(hashlib.shake_256(pickle.dumps(objs)).digest(32)) if want_alpha else None
+                if not want_alpha:
+                    return None
+                return 12345678901234567890 if constant else O.sample(hashlib.shake_256(pickle.dumps(objs)).digest(32))
             eng.fri_commit(cw, rounds, off0, omega0, on_root)
             return objs
         fri_commit()
         torch.cuda.synchronize()
+        reps = 5
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(reps):
             roots = fri_commit()
         torch.cuda.synchronize()
-        fri_ms = (time.perf_counter() - t0) / 3 * 1e3
+        fri_ms = (time.perf_counter() - t0) / reps * 1e3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fri_commit(constant=True)  # the same ladder without the pickle + shake_256 of the challenge
+        torch.cuda.synchronize()
+        fri_const_ms = (time.perf_counter() - t0) / reps * 1e3
         t0 = time.perf_counter()
         oroots, _, _ = O.fri_commit_np(cw.cpu().numpy().view(np.uint64), off0, omega0, 4, 64)
         fri_cpu_ms = (time.perf_counter() - t0) * 1e3
         assert roots == oroots, "FRI commit roots differ from the oracle"
+        # blake2b-only roof: register-resident chains of node compressions, 1024 threads per SM
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        b2_iters, b2_blocks = 400, sms * 4
+        b2_ms = lib.sa_microbench(4, 1, b2_iters, b2_blocks, 256)
+        if b2_ms > 0:
+            b2_peak = b2_iters * b2_blocks * 256 / (b2_ms * 1e-3)
 
-    # ---- the Python list API of the drop-in (list[FieldElement] in and out), one 2^20 transform
-    list_api_s = fri_list_api_s = None
+    # ---- the Python list API of the drop-in, one 2^20 transform / one 2^20 Fri.commit:
+    #      list[FieldElement] in (pack + upload) and, since round 2, a device-resident list out
+    list_api_s = fri_list_api_s = list_api_dev = None
     if rank == 0 and world == 1:
         import sa_host
         import sa_marshal
+        import sa_devlist
         import ntt as dropin_ntt
+        import fri as dropin_fri
         field = sa_host.algebra.Field.main()
         FE = sa_host.algebra.FieldElement
         vals = sa_marshal.unpack(x[:N].cpu().numpy(), field, FE)
-        t0 = time.perf_counter()
-        outl = dropin_ntt.ntt(FE(w, field), vals)
-        list_api_s = time.perf_counter() - t0
+        wfe = FE(w, field)
+
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps, r
+        list_api_s, outl = timed(lambda: dropin_ntt.ntt(wfe, vals))           # list in, device list out
         assert outl[12345].value == int(want[12345][0]) | (int(want[12345][1]) << 64)
-        # Fri.commit through the drop-in on a list of 2^20 FieldElements (pack + upload + 12 rounds)
-        import fri as dropin_fri
-        f = dropin_fri.Fri(field.generator(), FE(w, field), N, 4, 64)
-        t0 = time.perf_counter()
-        f.commit(vals, dropin_fri.ProofStream())
-        fri_list_api_s = time.perf_counter() - t0
+        chain_s, back = timed(lambda: dropin_ntt.intt(wfe, dropin_ntt.ntt(wfe, outl)))  # device list in and out
+        f = dropin_fri.Fri(field.generator(), wfe, N, 4, 64)
+        fri_list_api_s, _ = timed(lambda: f.commit(vals, dropin_fri.ProofStream()))      # list in
+        fri_dev_s, _ = timed(lambda: f.commit(outl, dropin_fri.ProofStream()))           # device list in
+        sa_devlist.ENABLED = False
+        plain_s, _ = timed(lambda: dropin_ntt.ntt(wfe, vals), reps=1)                     # round-1 behaviour
+        sa_devlist.ENABLED = True
+        list_api_dev = {"ntt_list_in_device_list_out_s": list_api_s, "ntt_plus_intt_device_lists_s": chain_s,
+                        "fri_commit_list_in_s": fri_list_api_s, "fri_commit_device_list_in_s": fri_dev_s,
+                        "ntt_list_in_list_out_s": plain_s,
+                        "note": "2^20 elements; 'list in' packs 2^20 FieldElement objects and uploads 16 MiB, 'list out' "
+                                "creates 2^20 objects; device lists (sa_devlist.DeviceCodeword) skip both"}
 
     if rank != 0:
         if dist is not None:
@@ -343,9 +412,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u128 mod p (4x u32 limbs, Montgomery)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "log_n": LOG_N, "batch_per_gpu": BATCH,
-                   "l2": "inputs larger than L2: %d MiB in + %d MiB out per step" % (BATCH * 16, BATCH * 16),
-                   "parallelism": "batch sharded across %d GPU(s), no collective in the timed region" % world},
+        "config": config_dict(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ntt_tile_kernel<10>", "launches_per_step": launches_per_step,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
@@ -362,8 +429,9 @@ def run_ours(args):
                          "how": "peak = sa_microbench: register-resident montmul+add+sub loop, 4 independent "
                                 "chains per thread, 1024 threads per SM, measured in this run"},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                         "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP); reference "
-                                   "pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
+                         "sample": "2 steps of %d x 2^20 ntt with oracle/stark_oracle.c (OpenMP tasks: transforms, "
+                                   "recursion and combine loops, so every one of the `cores` threads works); the "
+                                   "reference's pure-Python ntt is 5.5e4 butterflies/s on 1 core (BASELINE.md)" % BATCH},
         "cpu_python": {"value": py_value, "unit": UNIT, "cores": 1, "kind": "port",
                        "sample": "oracle.py py_ntt at n = 2^12; the reference's own ntt measured 3.9e4-6.4e4 "
                                  "butterflies/s at 2^10..2^20 on one Xeon core (BASELINE.md section 2)"},
@@ -374,7 +442,20 @@ def run_ours(args):
         "clocks": clocks,
         "single_ntt_us": single_us,
         "list_api_ntt_2_20_s": list_api_s, "list_api_fri_commit_2_20_s": fri_list_api_s,
+        "list_api": list_api_dev,
         "fri_commit_ms_2_20": fri_ms, "fri_commit_cpu_port_ms_2_20": fri_cpu_ms,
+        "fri_roofline": None if fri_ms is None else {
+            "bound": "alu pipe (blake2b: 64-bit add / xor / rotate), not HBM",
+            "achieved": FRI_COMPRESSIONS / (fri_ms * 1e-3), "peak": b2_peak, "unit": "blake2b compressions/s",
+            "frac": (FRI_COMPRESSIONS / (fri_ms * 1e-3) / b2_peak) if b2_peak else None,
+            "compressions_per_commit": FRI_COMPRESSIONS, "rounds": FRI_ROUNDS,
+            "ms_with_python_challenge": fri_ms, "ms_with_constant_challenge": fri_const_ms,
+            "hbm": {"algorithmic_bytes": FRI_ALG_BYTES, "achieved_gbs": FRI_ALG_BYTES / (fri_ms * 1e-3) / 1e9,
+                    "frac": FRI_ALG_BYTES / (fri_ms * 1e-3) / 1e9 / peak,
+                    "retained_tree_bytes": 64 * (4 * N - ((4 * N) >> FRI_ROUNDS))},
+            "how": "peak = sa_microbench(4): register-resident chains of single-block blake2b node compressions, 1024 "
+                   "threads per SM, measured in this run; achieved = 4 193 268 compressions (12 trees) / wall time of "
+                   "sa_fri_commit on a device-resident 2^20 codeword incl. the per-round host Fiat-Shamir"},
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -155,7 +155,8 @@ int sa_release_workspaces(void);
  * mismatches (0 = pass) or a negative SA_E* code.                                         */
 long long sa_selftest_field(size_t count, uint64_t seed);
 /* Micro-benchmark: n_threads threads each run `iters` dependent rounds of `ilp`
- * independent operations of kind op (0 montmul, 1 add, 2 sub, 3 butterfly).  Returns the
+ * independent operations of kind op (0 montmul, 1 add, 2 sub, 3 butterfly; 4 = blake2b node
+ * compressions, 256 threads per block whatever `threads` says, ilp 1 or 2).  Returns the
  * kernel time in milliseconds (negative on error).                                        */
 double sa_microbench(int op, int ilp, int iters, int blocks, int threads);
 

@@ -442,6 +442,28 @@ __global__ void k_microbench(fe *sink, int iters) {
     if (acc.v[0] == 0xDEADBEEFu && acc.v[1] == 0x1u) tile_st(sink + t, acc);
 }
 
+// blake2b-only roof of the Merkle kernels: every thread hashes a chain of node messages (128 bytes = one
+// compression each, merkle.py:11) that never leave its registers
+template <int ILP>
+__global__ void __launch_bounds__(MK_THREADS) k_microbench_b2(uint64_t *sink, int iters) {
+    uint64_t d[ILP][8];
+    const uint64_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < ILP; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[i][k] = t * 0x9E3779B97F4A7C15ull + 131 * i + k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) merkle_node_digest(d[i], d[i], d[(i + 1) % ILP]);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc ^= d[i][k];
+    if (acc == 0x1234567ull) sink[t] = acc;
+}
+
 // ------------------------------------------------------------- workspaces --
 // Grow-only scratch buffers, one per (device, stream): the four-step NTT needs an n*batch
 // intermediate and allocating it per call (even stream-ordered) costs more than the kernels.
@@ -1425,13 +1447,36 @@ static double microbench_op(int ilp, int iters, int blocks, int threads, fe *sin
 extern "C" {
 double sa_microbench(int op, int ilp, int iters, int blocks, int threads) {
     fe *sink = nullptr;
-    if (cudaMalloc(&sink, sizeof(fe) * (size_t)blocks * threads) != cudaSuccess) return -1.0;
+    if (cudaMalloc(&sink, sizeof(fe) * (size_t)blocks * (threads > MK_THREADS ? threads : MK_THREADS)) != cudaSuccess)
+        return -1.0;
     double ms = -1.0;
     switch (op) {
         case 0: ms = microbench_op<0>(ilp, iters, blocks, threads, sink); break;
         case 1: ms = microbench_op<1>(ilp, iters, blocks, threads, sink); break;
         case 2: ms = microbench_op<2>(ilp, iters, blocks, threads, sink); break;
         case 3: ms = microbench_op<3>(ilp, iters, blocks, threads, sink); break;
+        case 4: {  // blake2b node compressions (threads is fixed at MK_THREADS)
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            auto run = [&](int it) {
+                if (ilp >= 2)
+                    k_microbench_b2<2><<<blocks, MK_THREADS>>>((uint64_t *)sink, it);
+                else
+                    k_microbench_b2<1><<<blocks, MK_THREADS>>>((uint64_t *)sink, it);
+            };
+            run(iters / 8 + 1);
+            cudaEventRecord(e0);
+            run(iters);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float f = 0;
+            cudaEventElapsedTime(&f, e0, e1);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            ms = (double)f;
+            break;
+        }
     }
     g_launches.fetch_add(2);
     if (cudaGetLastError() != cudaSuccess) ms = -1.0;
