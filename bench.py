@@ -162,6 +162,70 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def allgather_leg(eng, dist, rank, world, w, reps=20):
+    """north_star's multi-GPU sentence on the clock: ONE batch of 16 x 2^20 transforms sharded over the N ranks
+    (strong scaling: 16 / N transforms per rank) INCLUDING the assembly of the whole batch on every rank, for every
+    assembly mode of sa_dist.sharded_ntt.  Device-timed (CUDA events around `reps` calls incl. the cross-rank fence),
+    max over ranks; rank 0 checks transforms it does not own against the oracle."""
+    import numpy as np
+    import torch
+    import oracle as O
+    import sa_dist
+    dev = eng.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)  # the SAME batch on every rank
+    lo = torch.randint(-(1 << 63), (1 << 63) - 1, (BATCH * N,), dtype=torch.int64, device=dev, generator=g)
+    hi = torch.randint(0, 0x4B80000000000000, (BATCH * N,), dtype=torch.int64, device=dev, generator=g)
+    xg = torch.stack([lo, hi], dim=1).contiguous()
+    del lo, hi
+    res = {"batch": BATCH, "log_n": LOG_N, "bytes_received_per_rank": (world - 1) * (BATCH // world) * N * 16, "modes": {}}
+    peers = None
+    try:
+        peers = sa_dist.PeerBuffers(BATCH * N)
+    except Exception as exc:  # no CUDA IPC in this container: the NCCL modes still run
+        res["peer_buffers_error"] = repr(exc)[:300]
+    check = sorted({BATCH - 1, BATCH // 2, 0})
+    want = {b: O.ntt_np(w, xg[b * N:(b + 1) * N].cpu().numpy().view(np.uint64), parallel=True) for b in check} if rank == 0 else {}
+    stream = torch.cuda.current_stream()
+    for mode in ("p2p-store", "p2p-copy", "nccl-pipelined", "nccl"):
+        if mode.startswith("p2p") and peers is None:
+            continue
+        try:
+            def call():
+                return sa_dist.sharded_ntt(xg, LOG_N, w, assemble=mode, peers=peers)
+            for _ in range(3):
+                full = call()
+            torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0:
+                got = full.cpu().numpy().view(np.uint64)
+                for b in check:
+                    assert (got[b * N:(b + 1) * N] == want[b]).all(), "assembled batch differs from the oracle (%s, %d)" % (mode, b)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ev0.record(stream)
+            for _ in range(reps):
+                full = call()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = torch.tensor([ev0.elapsed_time(ev1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["modes"][mode] = {"ms_per_call": float(t.item())}
+            del full
+        except Exception as exc:
+            res["modes"][mode] = {"error": repr(exc)[:300]}
+            torch.cuda.synchronize()
+    ok = {m: v["ms_per_call"] for m, v in res["modes"].items() if "ms_per_call" in v}
+    if ok:
+        best = min(ok, key=ok.get)
+        res.update({"mode": best, "ms_per_call": ok[best], "value": BATCH * BUTTERFLIES_PER_NTT / (ok[best] * 1e-3),
+                    "unit": UNIT, "scaling": "strong (one 16 x 2^20 batch over all ranks, result assembled on every rank)",
+                    "received_gbs_per_rank": res["bytes_received_per_rank"] / (ok[best] * 1e-3) / 1e9})
+    return res
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -373,6 +437,9 @@ def run_ours(args):
                         "note": "2^20 elements; 'list in' packs 2^20 FieldElement objects and uploads 16 MiB, 'list out' "
                                 "creates 2^20 objects; device lists (sa_devlist.DeviceCodeword) skip both"}
 
+    # ---- N > 1: the same batch sharded over the ranks WITH the assembly on every rank (every rank takes part)
+    with_allgather = allgather_leg(eng, dist, rank, world, w) if dist is not None else None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -438,6 +505,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * 16,
                 "d2h_bytes_per_step": BATCH * N * 16, "api": "sa_ntt_host (C ABI, host buffers from sa_host_alloc)",
                 "host_buffers": "page-locked, on the NUMA node of the rank's GPU (sa_host_alloc)"},
+        "with_allgather": with_allgather,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "single_ntt_us": single_us,

@@ -62,6 +62,16 @@ uint64_t sa_launch_count(void);
  * in == out is allowed.  log_n in [0, 26].                                               */
 int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
            void *stream);
+/* Multi-GPU assembly (no reference counterpart: the reference is one thread on one CPU).
+ * The same transforms, but the results are written to element offset `out_offset` of EVERY buffer
+ * outs[0 .. nouts), nouts <= 8: outs[0] is memory of the current device, the others are buffers of
+ * other GPUs mapped into this process (CUDA IPC / peer access over NVLink - stark-anatomy_b200/sa_dist.py
+ * does the mapping with torch).  The stores to the peers are issued by the last pass of the
+ * transform itself, tile by tile, so when every rank has run its shard of a batch each rank holds the
+ * whole batch and no gather pass follows.  Completion on the peers is the caller's to synchronise
+ * (a barrier across the ranks after the stream has drained).                                  */
+int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
+                 const uint64_t root[2], int inverse, size_t batch, void *stream);
 /* Same through HOST buffers: H2D copy, transforms, D2H copy, synchronises before
  * returning (the end-to-end call bench.py times as `e2e`).                               */
 int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,

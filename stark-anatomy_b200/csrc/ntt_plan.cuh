@@ -61,6 +61,7 @@ inline void ntt_fill_common(TileArgs &a) {
     a.scale = fe_mont_one();
     a.twb = nullptr;
     a.twb_stride = 0;
+    a.npeer = 0;
 }
 // three-pass split (see the header comment).  tmp: n * batch workspace; out doubles as the first
 // intermediate (a tile reads all of its elements before it writes them, so in == out is fine).

@@ -30,6 +30,8 @@
 
 namespace sa {
 
+constexpr int TILE_MAX_PEERS = 7;  // 8 GPUs per NVSwitch domain: self + 7
+
 struct TileArgs {
     const fe *in;
     fe *out;
@@ -46,11 +48,16 @@ struct TileArgs {
     int has_scale;
     fe scale;   // Montgomery-form scalar applied to every output when has_scale
     fe cst[8];  // cst[k] = w_16^k (Montgomery form) when L >= 16, else w_L^k; k < 8
+    // multi-GPU assembly (sa_ntt_multi): the last stage also stores every output to the same element
+    // offset of these peer buffers (device memory of other GPUs mapped over NVLink), so the result lands
+    // on every rank while it is being computed and no gather pass follows
+    fe *peer_out[TILE_MAX_PEERS];
+    int npeer;
 };
 
 // kernel variants: with TF_DYNAMIC everything is decided at run time (partial tiles, optional
 // output twiddle / scale); the static variants drop the predication and branches
-enum { TF_FULL = 1, TF_TWB = 2, TF_SCALE = 4, TF_DYNAMIC = 8 };
+enum { TF_FULL = 1, TF_TWB = 2, TF_SCALE = 4, TF_DYNAMIC = 8, TF_PEERS = 16 };
 
 template <int LOGL, int ELOG, int C>
 struct TilePlan {
@@ -294,7 +301,13 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
             fe v = x[k];
             if (use_twb && active) v = fe_montmul(v, tile_ldg(twb + o * twb_sr));
             if (use_scale) v = fe_montmul(v, a.scale);
-            if (active) tile_st(dst + o * out_sr, v);
+            if (active) {
+                tile_st(dst + o * out_sr, v);
+                if constexpr ((FLAGS & TF_PEERS) != 0) {
+                    const long long rel = (dst - a.out) + (long long)(o * out_sr);
+                    for (int pi = 0; pi < a.npeer; pi++) tile_st(a.peer_out[pi] + rel, v);
+                }
+            }
         }
     }
 }
@@ -320,7 +333,9 @@ template <int LOGL, int ELOG, int C>
 SA_HD int tile_variant(const TileArgs &a) {
     using P = TilePlan<LOGL, ELOG, C>;
     const long long tiles = (long long)((a.ncols + C - 1) / C) * a.nbatch;
-    if (LOGL < 5 || a.ncols % C != 0 || tiles % P::TPC != 0 || a.has_scale) return TF_DYNAMIC;
+    const int peers = a.npeer > 0 ? TF_PEERS : 0;
+    if (LOGL < 5 || a.ncols % C != 0 || tiles % P::TPC != 0 || a.has_scale) return TF_DYNAMIC | peers;
+    if (peers) return a.twb == nullptr ? (TF_FULL | TF_PEERS) : (TF_DYNAMIC | TF_PEERS);
     return TF_FULL | (a.twb != nullptr ? TF_TWB : 0);
 }
 

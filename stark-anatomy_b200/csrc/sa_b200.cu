@@ -713,12 +713,15 @@ static int launch_tile_variant(const TileArgs &a, cudaStream_t st) {
 }
 template <int LOGL, int ELOG, int C>
 static int launch_tile(const TileArgs &a, cudaStream_t st) {
+    const int variant = tile_variant<LOGL, ELOG, C>(a);
     if constexpr (LOGL >= 5) {
-        switch (tile_variant<LOGL, ELOG, C>(a)) {
+        switch (variant) {
             case TF_FULL | TF_TWB: return launch_tile_variant<LOGL, ELOG, C, TF_FULL | TF_TWB>(a, st);
             case TF_FULL: return launch_tile_variant<LOGL, ELOG, C, TF_FULL>(a, st);
+            case TF_FULL | TF_PEERS: return launch_tile_variant<LOGL, ELOG, C, TF_FULL | TF_PEERS>(a, st);
         }
     }
+    if (variant & TF_PEERS) return launch_tile_variant<LOGL, ELOG, C, TF_DYNAMIC | TF_PEERS>(a, st);
     return launch_tile_variant<LOGL, ELOG, C, TF_DYNAMIC>(a, st);
 }
 
@@ -773,14 +776,19 @@ const char *sa_version(void) { return "sa_b200 0.1 sm_100a"; }
 const char *sa_last_error(void) { return g_last_error.c_str(); }
 uint64_t sa_launch_count(void) { return g_launches.load(); }
 
-int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
-           void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+// the transform proper; `peers` (npeer <= TILE_MAX_PEERS) are extra destinations of the LAST pass: the
+// same element offsets as `out`, in other GPUs' memory (sa_ntt_multi)
+static int ntt_run(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
+                   cudaStream_t st, fe *const *peers, int npeer) {
     if (log_n < 0 || log_n > NTT_MAX_LOG_N) return SA_ESIZE;
     if (batch == 0) return SA_OK;
     const size_t n = size_t(1) << log_n;
     if (log_n == 0) {  // ntt.py:5-6 / :23-24: a length-1 sequence is returned as is
         if (out != in) SA_CUDA(cudaMemcpyAsync(out, in, 16 * batch, cudaMemcpyDeviceToDevice, st));
+        for (int i = 0; i < npeer; i++)
+            SA_CUDA(cudaMemcpyAsync(peers[i], in, 16 * batch, cudaMemcpyDeviceToDevice, st));
         return SA_OK;
     }
     PlanPtr p;  // keeps the tables alive until the launches below are enqueued (cudaFree waits for them)
@@ -788,11 +796,16 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     if (rc != SA_OK) return rc;
     TileArgs a;
     memset(&a, 0, sizeof(a));
+    auto with_peers = [&](TileArgs &t) {
+        t.npeer = npeer;
+        for (int i = 0; i < npeer; i++) t.peer_out[i] = peers[i];
+    };
     if (log_n <= 10) {
         // every transform is one tile column; in-place is safe because a tile reads all of
         // its columns into registers before it writes any of them
         if (batch > (size_t)1 << 30) return SA_ESIZE;
         ntt_fill_single(a, (const fe *)in, (fe *)out, log_n, batch, p->tw1, p->cst1, p->has_scale, p->scale_m);
+        with_peers(a);
         return launch_tile_dyn(log_n, a, st);
     }
     NttShape shape;
@@ -810,15 +823,33 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
         ntt_fill_3pass_b(a, (const fe *)out, tmp, shape, batch, p->tw2, p->twb2, p->cst2);
         if ((rc = launch_tile_dyn(p->l2, a, st)) != SA_OK) return rc;
         ntt_fill_3pass_c(a, tmp, (fe *)out, shape, batch, p->tw3, p->cst3);
+        with_peers(a);
         return launch_tile_dyn(p->l3, a, st);
     }
     ntt_fill_pass1(a, (const fe *)in, tmp, shape, batch, p->tw1, p->twb, p->cst1);
     rc = launch_tile_dyn(p->l1, a, st);
     if (rc == SA_OK) {
         ntt_fill_pass2(a, tmp, (fe *)out, shape, batch, p->tw2, p->cst2);
+        with_peers(a);
         rc = launch_tile_dyn(p->l2, a, st);
     }
     return rc;
+}
+
+extern "C" {
+
+int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
+           void *stream) {
+    return ntt_run(out, in, log_n, root, inverse, batch, (cudaStream_t)stream, nullptr, 0);
+}
+
+int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
+                 const uint64_t root[2], int inverse, size_t batch, void *stream) {
+    if (nouts < 1 || nouts > TILE_MAX_PEERS + 1) return SA_ESIZE;
+    fe *peers[TILE_MAX_PEERS];
+    for (int i = 1; i < nouts; i++) peers[i - 1] = (fe *)outs[i] + out_offset;
+    return ntt_run((fe *)outs[0] + out_offset, in, log_n, root, inverse, batch, (cudaStream_t)stream, peers,
+                   nouts - 1);
 }
 
 // Host entry: H2D, transforms, D2H.  Batches are cut into chunks of a few transforms that rotate over

@@ -2,10 +2,23 @@
 
 The hot path shards at batch level: independent transforms (one per polynomial / register /
 column) and independent FRI instances have no data dependence, so every rank (one process per
-GPU, ``torch.distributed``) runs its slice of the batch with no communication, and ONE
-all-gather assembles the outputs where the caller wants them on every rank (NCCL over
-NVLink / NVSwitch on GPUs; gloo for the CPU tests).  A single transform or a single FRI commit
-is not split: FRI rounds are sequential through the host Fiat-Shamir challenge.
+GPU, ``torch.distributed``) runs its slice of the batch with no communication during compute.
+What is left is ASSEMBLY: the caller wants the transformed batch on every rank.  Four ways to do
+it, all bit-exact (``assemble=`` of ``sharded_ntt``):
+
+  "p2p-store"  the product.  Every rank maps the other ranks' output buffers (CUDA IPC over NVLink /
+               NVSwitch, ``PeerBuffers``) and the LAST pass of its transforms stores each result tile
+               to all of them (``sa_ntt_multi``): compute and assembly are one kernel, the NVLink
+               writes overlap the butterflies tile by tile, no gather pass exists.
+  "p2p-copy"   transforms go to the local buffer; as soon as transform i is done the copy engines push it
+               to every peer (one stream per peer) while transform i+1 computes.
+  "nccl-pipelined"  cyclic ownership (rank r owns transforms r, r + world, ...), so chunk i of every rank
+               is one in-place ``all_gather_into_tensor`` that runs on a side stream under chunk i+1.
+  "nccl"       round 1's baseline: transform the contiguous slice, then ONE all-gather (also the only mode for
+               ragged batches and for the gloo backend of the CPU tests).
+
+A single transform or a single FRI commit is not split: FRI rounds are sequential through the host
+Fiat-Shamir challenge.  Independent FRI instances shard like transforms (``sharded_fri_commit``).
 """
 import numpy as np
 
@@ -24,38 +37,172 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
-def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None):
-    """Transform a batch of B independent 2^log_n-point vectors, B split across the ranks.
+def _rank_world(group=None):
+    dist = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+# --------------------------------------------------------------------------- peer-mapped buffers
+class PeerBuffers:
+    """``count`` symmetric device buffers of ``nelems`` field elements, each mapped on every rank.
+
+    Rank r allocates its buffers with torch, exports them as CUDA IPC handles
+    (``torch.multiprocessing.reductions.reduce_tensor``), the handles travel through
+    ``all_gather_object`` and every other rank opens them (peer access over NVLink is enabled by
+    the open).  ``bufs[k][q]`` is rank q's k-th buffer as a tensor usable from THIS process.
+    Two buffers alternate between calls so that a rank may still read call k's result while
+    another rank already writes call k+1 (see ``sharded_ntt``).
+    """
+
+    def __init__(self, nelems, group=None, count=2):
+        import torch
+        from torch.multiprocessing.reductions import reduce_tensor
+        dist = _dist()
+        eng = sa_engine.get_engine()
+        self.group = group
+        self.rank, self.world = _rank_world(group)
+        self.nelems = nelems
+        self.local = [torch.zeros((nelems, 2), dtype=torch.int64, device=eng.device) for _ in range(count)]
+        self.bufs = []
+        for k in range(count):
+            if self.world == 1:
+                self.bufs.append([self.local[k]])
+                continue
+            handles = [None] * self.world
+            dist.all_gather_object(handles, reduce_tensor(self.local[k]), group=group)
+            row = []
+            for q, (fn, args) in enumerate(handles):
+                row.append(self.local[k] if q == self.rank else fn(*args))
+            self.bufs.append(row)
+        self.turn = 0
+        self.flag = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        self.side = None
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=group)  # every rank has opened every handle before anybody writes
+
+    def next(self):
+        """(local buffer, [rank q's buffer for q in range(world)]) of this call"""
+        k = self.turn
+        self.turn = (self.turn + 1) % len(self.local)
+        return self.local[k], self.bufs[k]
+
+    def fence(self):
+        """stream-ordered barrier across the ranks (a 4-byte NCCL all-reduce on the current stream): when it
+        has passed on this rank, every rank has finished the kernels / copies it enqueued before its own"""
+        if self.world > 1:
+            _dist().all_reduce(self.flag, group=self.group)
+
+    def streams(self):
+        import torch
+        if self.side is None:
+            self.side = [torch.cuda.Stream() for _ in range(self.world)]
+            self.events = [torch.cuda.Event() for _ in range(self.world + 1)]
+        return self.side
+
+
+# ------------------------------------------------------------------------------- sharded transforms
+def owner_cyclic(b, world):
+    return b % world
+
+
+def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None, assemble="nccl", peers=None):
+    """Transform a batch of B independent 2^log_n-point vectors, B split across the ranks
+    (code/ntt.py:3-30 per transform).
 
     vectors: engine vector of B*n elements (every rank passes the same batch, or at least its own
-    slice filled in).  Returns the full batch on every rank when ``gather`` (one all-gather),
-    else only this rank's transformed slice.  code/ntt.py:3-30 per transform.
+    slice filled in).  Returns the full batch on every rank when ``gather`` (see the module docstring
+    for ``assemble``), else only this rank's transformed slice.  The p2p modes need ``peers`` (a
+    ``PeerBuffers`` of B*n elements, reusable across calls) and an even split; the returned tensor is
+    one of its buffers and is overwritten by the call after the next one.
     """
     eng = sa_engine.get_engine()
-    dist = _dist()
     n = 1 << log_n
     batch = eng.length(vectors) // n
-    rank = dist.get_rank(group) if dist else 0
-    world = dist.get_world_size(group) if dist else 1
-    lo, hi = shard_range(batch, rank, world)
-    local = eng.ntt(eng.slice(vectors, lo * n, hi * n), log_n, root, inverse=inverse, batch=hi - lo) \
-        if hi > lo else eng.empty(0)
-    if not gather or world == 1:
-        return local
-    return all_gather_vectors(local, [shard_range(batch, r, world) for r in range(world)], n, group)
+    rank, world = _rank_world(group)
+    if not gather or world == 1 or assemble == "nccl" or batch % world != 0:
+        lo, hi = shard_range(batch, rank, world)
+        local = eng.ntt(eng.slice(vectors, lo * n, hi * n), log_n, root, inverse=inverse, batch=hi - lo) \
+            if hi > lo else eng.empty(0)
+        if not gather or world == 1:
+            return local
+        return all_gather_vectors(local, [shard_range(batch, r, world) for r in range(world)], n, group)
+    per = batch // world
+    if assemble == "nccl-pipelined":
+        return _ntt_nccl_pipelined(eng, vectors, log_n, root, inverse, n, per, rank, world, group)
+    if peers is None:
+        raise ValueError("assemble=%r needs peers=PeerBuffers(batch * n)" % assemble)
+    lo = rank * per
+    mine = eng.slice(vectors, lo * n, (lo + per) * n)
+    local, bufs = peers.next()
+    if assemble == "p2p-store":
+        outs = [local] + [bufs[q] for q in range(world) if q != rank]
+        eng.ntt_multi(outs, lo * n, mine, log_n, root, inverse=inverse, batch=per)
+    elif assemble == "p2p-copy":
+        _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world)
+    else:
+        raise ValueError("unknown assemble mode %r" % assemble)
+    peers.fence()
+    return local
+
+
+def _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world):
+    import torch
+    side = peers.streams()
+    main = torch.cuda.current_stream()
+    for i in range(per):
+        dst = local[(lo + i) * n:(lo + i + 1) * n]
+        eng.ntt_into(dst, mine[i * n:(i + 1) * n], log_n, root, inverse=inverse)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for q in range(world):
+            if q == rank:
+                continue
+            with torch.cuda.stream(side[q]):
+                side[q].wait_event(ev)
+                bufs[q][(lo + i) * n:(lo + i + 1) * n].copy_(dst, non_blocking=True)
+    for q in range(world):
+        if q != rank:
+            main.wait_stream(side[q])
+
+
+def _ntt_nccl_pipelined(eng, vectors, log_n, root, inverse, n, per, rank, world, group):
+    import torch
+    dist = _dist()
+    out = eng.empty(per * world * n)
+    main = torch.cuda.current_stream()
+    comm = torch.cuda.Stream()
+    works = []
+    for i in range(per):
+        b = i * world + rank  # cyclic ownership: chunk i of every rank is contiguous in batch order
+        dst = out[b * n:(b + 1) * n]
+        eng.ntt_into(dst, vectors[b * n:(b + 1) * n], log_n, root, inverse=inverse)
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            works.append(dist.all_gather_into_tensor(out[i * world * n:(i + 1) * world * n], dst, group=group,
+                                                     async_op=True))
+    for wk in works:
+        wk.wait()
+    main.wait_stream(comm)
+    return out
 
 
 def all_gather_vectors(local, ranges, n, group=None):
     """one all-gather of per-rank slices (padded to the largest slice) -> concatenated batch"""
     import torch
     dist = _dist()
-    eng = sa_engine.get_engine()
     world = len(ranges)
     longest = max(hi - lo for lo, hi in ranges) * n
     is_torch = isinstance(local, torch.Tensor)
     t = local if is_torch else torch.from_numpy(np.ascontiguousarray(local).view(np.int64))
-    pad = torch.zeros((longest, 2), dtype=torch.int64, device=t.device)
-    pad[:t.shape[0]] = t
+    even = all(hi - lo == ranges[0][1] - ranges[0][0] for lo, hi in ranges)
+    if even and t.shape[0] == longest:
+        pad = t.contiguous()
+    else:
+        pad = torch.zeros((longest, 2), dtype=torch.int64, device=t.device)
+        pad[:t.shape[0]] = t
     out = torch.empty((world * longest, 2), dtype=torch.int64, device=t.device)
     if t.is_cuda:
         dist.all_gather_into_tensor(out, pad, group=group)
@@ -63,11 +210,14 @@ def all_gather_vectors(local, ranges, n, group=None):
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad, group=group)
         out = torch.cat(parts, dim=0)
-    pieces = [out[r * longest:r * longest + (hi - lo) * n] for r, (lo, hi) in enumerate(ranges)]
-    full = torch.cat(pieces, dim=0)
+    if even:
+        full = out
+    else:
+        full = torch.cat([out[r * longest:r * longest + (hi - lo) * n] for r, (lo, hi) in enumerate(ranges)], dim=0)
     return full if is_torch else full.numpy().view(np.uint64)
 
 
+# ---------------------------------------------------------------------------- Merkle / FRI instances
 def sharded_merkle_roots(vectors, n, group=None):
     """Merkle roots (code/merkle.py:13-14) of a batch of B independent n-element codewords, B split
     across the ranks; the 64-byte roots are all-gathered (B * 64 bytes in total).  Returns list[bytes]."""
@@ -75,8 +225,7 @@ def sharded_merkle_roots(vectors, n, group=None):
     eng = sa_engine.get_engine()
     dist = _dist()
     batch = eng.length(vectors) // n
-    rank = dist.get_rank(group) if dist else 0
-    world = dist.get_world_size(group) if dist else 1
+    rank, world = _rank_world(group)
     lo, hi = shard_range(batch, rank, world)
     mine = [eng.tree_root(eng.merkle_tree(eng.slice(vectors, b * n, (b + 1) * n))) for b in range(lo, hi)]
     if world == 1:
@@ -95,3 +244,35 @@ def sharded_merkle_roots(vectors, n, group=None):
         l, h = shard_range(batch, r, world)
         roots += [bytes(parts[r][i].cpu().numpy().tobytes()) for i in range(h - l)]
     return roots
+
+
+def sharded_fri_commit(codewords, fri, make_stream=None, group=None):
+    """``Fri.commit`` (code/fri.py:56-96) of B INDEPENDENT instances, B split across the ranks.
+
+    codewords : list of B codewords of ``fri.domain_length`` elements each (lists of FieldElement,
+                DeviceCodeword objects or engine vectors wrapped by the caller); every rank passes the same list
+                and only reads its own shard.
+    fri       : the drop-in ``fri.Fri`` instance (same parameters for every instance).
+    make_stream(b) -> the proof stream object of instance b (default: a fresh ``ProofStream``); every
+                instance has its own transcript, so its challenges depend on its own roots only.
+    Returns, on every rank, ``[objects_0, ..., objects_{B-1}]``: what instance b's commit pushed into its
+    proof stream (the round roots, then the last codeword) -- gathered with one ``all_gather_object``
+    (a few KB per instance; the big layers and trees stay on the rank that owns the instance).
+    Rounds of ONE commit stay sequential (host Fiat-Shamir); nothing is split inside an instance.
+    """
+    import sa_host
+    dist = _dist()
+    rank, world = _rank_world(group)
+    batch = len(codewords)
+    lo, hi = shard_range(batch, rank, world)
+    mine = []
+    for b in range(lo, hi):
+        ps = make_stream(b) if make_stream is not None else sa_host.ip.ProofStream()
+        before = len(ps.objects)
+        fri.commit(codewords[b], ps)
+        mine.append(ps.objects[before:])
+    if world == 1:
+        return mine
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    return [objs for part in parts for objs in part]

@@ -36,6 +36,7 @@ SYMBOLS = [
     ("sa_last_error", ctypes.c_char_p, []),
     ("sa_launch_count", ctypes.c_uint64, []),
     ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_ntt_multi", _ci, [ctypes.POINTER(ctypes.c_void_p), _ci, _sz, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_host_alloc", _vp, [_sz]),
     ("sa_host_free", _ci, [_vp]),
@@ -163,6 +164,21 @@ class CudaEngine:
         self._check(self.lib.sa_ntt(out.data_ptr(), vec.data_ptr(), log_n, _limbs(root), int(bool(inverse)),
                                     batch, self._stream()))
         return out
+
+    def ntt_into(self, out, vec, log_n, root, inverse=False, batch=1):
+        """sa_ntt into a caller-provided device vector (a slice of a larger buffer); out may alias vec"""
+        assert out.is_contiguous() and vec.is_contiguous() and out.shape[0] == vec.shape[0]
+        self._check(self.lib.sa_ntt(out.data_ptr(), vec.data_ptr(), log_n, _limbs(root), int(bool(inverse)), batch,
+                                    self._stream()))
+        return out
+
+    def ntt_multi(self, outs, out_offset, vec, log_n, root, inverse=False, batch=1):
+        """sa_ntt_multi: transform `vec` and store the result at element offset `out_offset` of every tensor in
+        `outs` (outs[0] on this device, the others peer-mapped buffers of other GPUs)"""
+        vec = vec.contiguous()
+        ptrs = (ctypes.c_void_p * len(outs))(*[int(t.data_ptr()) for t in outs])
+        self._check(self.lib.sa_ntt_multi(ptrs, len(outs), out_offset, vec.data_ptr(), log_n, _limbs(root),
+                                          int(bool(inverse)), batch, self._stream()))
 
     def pointwise_mul(self, a, b):
         out = self.empty(a.shape[0])

@@ -63,6 +63,10 @@ class OracleEngine:
         except AssertionError as e:
             raise SaError(str(e))
 
+    def ntt_into(self, out, vec, log_n, root, inverse=False, batch=1):
+        out[:] = self.ntt(vec, log_n, root, inverse=inverse, batch=batch)
+        return out
+
     def pointwise_mul(self, a, b):
         self._log("pointwise_mul", a.shape[0])
         return O.pointwise_mul_np(np.ascontiguousarray(a), np.ascontiguousarray(b))

@@ -43,6 +43,22 @@ def _worker(rank, world, port, batch, log_n, q):
     ok = ok and bool((back == x).all())
     roots = sa_dist.sharded_merkle_roots(x, n)
     ok = ok and roots == [O.merkle_root_np(x[b * n:(b + 1) * n]) for b in range(batch)]
+    # independent FRI instances: every rank commits its shard, the transcripts are gathered
+    import pickle
+    import fri as F
+    from hostmirror_loader import load_host_types
+    T = load_host_types()
+    m = 64
+    f = F.Fri(T.field.generator(), T.field.primitive_nth_root(m), m, 2, 4)
+    cws = [[T.fe(int(v[0]) | (int(v[1]) << 64)) for v in x[b * m:(b + 1) * m]] for b in range(batch)]
+    got = sa_dist.sharded_fri_commit(cws, f)
+    ok = ok and len(got) == batch
+    for b in range(batch):
+        ps = F.ProofStream()
+        F.Fri(T.field.generator(), T.field.primitive_nth_root(m), m, 2, 4).commit(cws[b], ps)
+        ok = ok and pickle.dumps(got[b]) == pickle.dumps(ps.objects)
+        oroots, _, _ = O.fri_commit_np(x[b * m:(b + 1) * m], O.GENERATOR, O.primitive_nth_root(m), 2, 4)
+        ok = ok and [o for o in got[b] if isinstance(o, bytes)] == oroots
     q.put((rank, ok, sa_engine.get_engine().calls[0]))
     dist.destroy_process_group()
 

@@ -182,6 +182,34 @@ def test_ntt_in_place_and_host_entry(eng):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("log_n,batch,nouts", [(0, 3, 2), (3, 5, 3), (8, 7, 2), (10, 4, 8), (14, 3, 3), (20, 2, 8),
+                                               (21, 1, 2)])
+def test_ntt_multi_stores_every_destination(eng, log_n, batch, nouts):
+    """sa_ntt_multi (multi-GPU assembly, sa_dist "p2p-store"): the last pass stores every result to the same
+    offset of all destination buffers.  Here all destinations are on this device (on the 8-GPU box the others
+    are peer-mapped buffers of the other ranks, tools/dist_check.py): each must equal the oracle's batch,
+    everything outside the written range must stay untouched, forward and inverse."""
+    import torch
+    n = 1 << log_n
+    w = O.primitive_nth_root(n) if n > 1 else 1
+    x = rand_np(4000 + log_n, n * batch)
+    want = O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2) if n > 1 else x
+    pad = 5 * n + 3
+    outs = [torch.full((pad + n * batch + 7, 2), -1, dtype=torch.int64, device=eng.device) for _ in range(nouts)]
+    eng.ntt_multi(outs, pad, up(eng, x), log_n, w, batch=batch)
+    for o in outs:
+        got = down(eng, o)
+        assert (got[pad:pad + n * batch] == want).all()
+        assert (got[:pad] == np.uint64(2**64 - 1)).all() and (got[pad + n * batch:] == np.uint64(2**64 - 1)).all()
+    if n > 1:
+        back = [torch.zeros((n * batch, 2), dtype=torch.int64, device=eng.device) for _ in range(nouts)]
+        eng.ntt_multi(back, 0, outs[-1][pad:pad + n * batch], log_n, w, inverse=True, batch=batch)
+        for b in back:
+            assert (down(eng, b) == x).all()
+    with pytest.raises(AssertionError, match="unsupported size"):
+        eng.ntt_multi(outs * 9, 0, up(eng, x), log_n, w, batch=batch)
+
+
 @pytest.mark.parametrize("log_n,batch", [(16, 70), (18, 9), (12, 3), (21, 3), (22, 2)])
 def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
     """sa_ntt_host cuts a batch into ramped chunks over several copy streams (32 MiB chunks, first and
