@@ -98,11 +98,15 @@ int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points
                  void *stream);
 
 /* code/ntt.py:66-80 fast_zerofier: out[0..k] = coefficients of prod_i (X - domain[i]) (monic,
- * k + 1 coefficients).  k <= 4096 per call (larger domains: split and fast_multiply).       */
+ * k + 1 coefficients), k <= 2^20.  Small domains: one kernel; larger ones: the subproduct tree of
+ * the reference, built level by level on the device with batched transforms (all nodes of a level
+ * in one sa_ntt call).                                                                       */
 int sa_zerofier(void *out, const void *domain, size_t k, void *stream);
 /* code/ntt.py:102-130 fast_interpolate: out[0..k) = coefficients of the polynomial of degree
- * < k with value values[i] at domain[i].  SA_EDIVZERO when two domain points coincide (the
- * reference's element-wise division asserts there).  k <= 4096; synchronises.               */
+ * < k with value values[i] at domain[i], k <= 2^20.  SA_EDIVZERO when two domain points coincide
+ * (the reference's element-wise division asserts there).  Small k: Lagrange kernels; larger k:
+ * zerofier tree, weights v_i / M'(d_i), and a bottom-up combination over the same tree - one call,
+ * everything on the device.  Synchronises.                                                    */
 int sa_interpolate(void *out, const void *domain, const void *values, size_t k, void *stream);
 
 /* ---- code/merkle.py:6-14 Merkle.commit -------------------------------------------------

@@ -261,6 +261,84 @@ __global__ void __launch_bounds__(256) k_interp_colsum(fe *out, const fe *QT, in
     }
     if (tid == 0) tile_st(out + m, red[0]);
 }
+// ---- subproduct tree over a domain of k points (fast_zerofier / fast_interpolate, ntt.py:66-130) ----
+// The k points sit in the first k of K = 2^ceil(log2 k) leaf slots.  Level j has K >> j nodes of
+// m = 2^j coefficients each, stored back to back.  A node whose leaf range lies completely inside the
+// domain is FULL: its zerofier is monic of degree exactly m and only the low m coefficients are stored
+// (the leading 1 is implied).  Any other node is stored EXPLICITLY (degree < m, all coefficients); a node
+// without points is the constant 1.  With child vectors vL, vR a parent is
+//     cyclic_product_2m(vL, vR) + x^m * ([L full] vR + [R full] vL)
+// (the cyclic product of size 2m never wraps: both factors have degree < m), FULL iff both children are.
+__device__ __forceinline__ bool tree_full(long long node, int mlog, long long k) { return ((node + 1) << mlog) <= k; }
+__global__ void k_tree_leaves(fe *v0, const fe *domain, long long k, long long K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) tile_st(v0 + i, i < k ? fe_neg(tile_ld(domain + i)) : fe_one());
+}
+// dst node (2m slots) = [src node (m coefficients), m zeros]
+__global__ void k_tree_pad(fe *dst, const fe *src, long long K, int mlog) {
+    const long long stride = (long long)gridDim.x * blockDim.x, m = 1ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * K; idx += stride) {
+        const long long node = idx >> (mlog + 1), t = idx & (2 * m - 1);
+        tile_st(dst + idx, t < m ? tile_ld(src + node * m + t) : fe_zero());
+    }
+}
+// transformed children (blocks of 2m) -> transformed parents: out[p][t] = in[2p][t] * in[2p+1][t]
+__global__ void k_tree_pairmul(fe *out, const fe *in, long long K, int mlog) {
+    const long long stride = (long long)gridDim.x * blockDim.x, two_m = 2ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < K; idx += stride) {
+        const long long p = idx >> (mlog + 1), t = idx & (two_m - 1);
+        const fe a = tile_ld(in + (2 * p) * two_m + t), b = tile_ld(in + (2 * p + 1) * two_m + t);
+        tile_st(out + idx, fe_montmul(fe_to_mont(a), b));
+    }
+}
+// interpolation up-sweep: out[p][t] = P[2p][t] * V[2p+1][t] + P[2p+1][t] * V[2p][t]
+__global__ void k_tree_cross(fe *out, const fe *Pt, const fe *Vt, long long K, int mlog) {
+    const long long stride = (long long)gridDim.x * blockDim.x, two_m = 2ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < K; idx += stride) {
+        const long long p = idx >> (mlog + 1), t = idx & (two_m - 1);
+        const long long l = (2 * p) * two_m + t, r = (2 * p + 1) * two_m + t;
+        const fe a = fe_montmul(fe_to_mont(tile_ld(Pt + l)), tile_ld(Vt + r));
+        const fe b = fe_montmul(fe_to_mont(tile_ld(Pt + r)), tile_ld(Vt + l));
+        tile_st(out + idx, fe_add(a, b));
+    }
+}
+// parent[p][m + t] += [L full] right[t] + [R full] left[t]; (left, right) = the child vectors of `add`
+// (the zerofier tree adds the children's own vectors, the interpolation sweep the OTHER tree's: P_L * M_R
+// picks up x^m * P_L when M_R is full, so `swap` exchanges the roles)
+__global__ void k_tree_fix(fe *parent, const fe *add, long long K, int mlog, long long k, int swap) {
+    const long long stride = (long long)gridDim.x * blockDim.x, m = 1ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < K / 2; idx += stride) {
+        const long long p = idx >> mlog, t = idx & (m - 1);
+        const bool lfull = tree_full(2 * p, mlog, k), rfull = tree_full(2 * p + 1, mlog, k);
+        if (!lfull && !rfull) continue;
+        const fe left = tile_ld(add + (2 * p) * m + t), right = tile_ld(add + (2 * p + 1) * m + t);
+        fe acc = tile_ld(parent + p * 2 * m + m + t);
+        if (swap) {
+            if (rfull) acc = fe_add(acc, left);
+            if (lfull) acc = fe_add(acc, right);
+        } else {
+            if (lfull) acc = fe_add(acc, right);
+            if (rfull) acc = fe_add(acc, left);
+        }
+        tile_st(parent + p * 2 * m + m + t, acc);
+    }
+}
+// out[i] = (i + 1) * z[i + 1], i < k  (formal derivative of a polynomial with k + 1 coefficients)
+__global__ void k_derivative(fe *out, const fe *z, long long k) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) tile_st(out + i, fe_montmul(fe_to_mont(fe_from_u64((uint64_t)(i + 1))), tile_ld(z + i + 1)));
+}
+// leaves of the interpolation sweep: q_i = v_i / M'(d_i) for i < k, 0 for the empty slots
+__global__ void k_tree_qleaves(fe *P0, const fe *q, long long k, long long K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) tile_st(P0 + i, i < k ? tile_ld(q + i) : fe_zero());
+}
+// zerofier coefficients from the tree's root vector: k == K -> implied leading 1
+__global__ void k_tree_root(fe *out, const fe *root, long long k, long long K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= k) tile_st(out + i, (i == K) ? fe_one() : tile_ld(root + i));
+}
+
 __global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xinv, fe s_m, fe inv2_m) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
@@ -1092,24 +1170,112 @@ int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points
     return SA_OK;
 }
 
+}  // extern "C"
+
+// ---- subproduct tree on the device (see the kernels above) ----
+constexpr int TREE_MAX_LOG = 20;  // 2^20 points: ~1 GiB of tree, transforms and scratch
+static int g_zf_direct_max = 512;       // up to here the one-CTA sweep kernel (SA_ZF_DIRECT_MAX with -DSA_TUNE)
+static int g_interp_direct_max = 1024;  // up to here the k x k Lagrange kernels (SA_INTERP_DIRECT_MAX)
+static void tree_config() {
+#ifdef SA_TUNE
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char *e = getenv("SA_ZF_DIRECT_MAX")) g_zf_direct_max = atoi(e);
+        if (const char *e = getenv("SA_INTERP_DIRECT_MAX")) g_interp_direct_max = atoi(e);
+    });
+#endif
+}
+// primitive 2^log-th root of unity: generator^(2^119 / 2^log), algebra.py:100-114
+static void tree_root_of_unity(uint64_t out[2], int log) {
+    // algebra.py:100-102: generator 85408008396924667383611388730472331217 has order 2^119
+    const uint64_t g[2] = {0xb5038f9c18f6f7d1ull, 0x4040fbed12ee470full};
+    fe w = fe_to_mont(fe_from_limbs(g));
+    for (int i = 119; i > log; i--) w = fe_montmul(w, w);
+    const fe c = fe_from_mont(w);
+    out[0] = (uint64_t)c.v[0] | ((uint64_t)c.v[1] << 32);
+    out[1] = (uint64_t)c.v[2] | ((uint64_t)c.v[3] << 32);
+}
+struct PolyTree {
+    int logK = 0;
+    long long k = 0, K = 0;
+    fe *levels = nullptr;      // (logK + 1) * K: level j at levels + j * K
+    fe *transforms = nullptr;  // logK * 2K: level j's node vectors zero-padded to 2m and transformed (or nullptr)
+    fe *scratch = nullptr;     // 2K
+};
+static inline unsigned tree_grid(long long n) {
+    long long g = (n + 255) / 256;
+    return (unsigned)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+// builds every level of the zerofier tree of domain[0..k) in `t` (buffers already assigned)
+static int tree_build(PolyTree &t, const fe *domain, cudaStream_t st) {
+    const long long K = t.K;
+    int rc;
+    k_tree_leaves<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(t.levels, domain, t.k, K);
+    SA_LAUNCH_CHECK();
+    for (int j = 0; j < t.logK; j++) {
+        uint64_t root[2];
+        tree_root_of_unity(root, j + 1);
+        fe *T = t.transforms ? t.transforms + (size_t)j * 2 * K : t.scratch;
+        fe *child = t.levels + (size_t)j * K, *parent = t.levels + (size_t)(j + 1) * K;
+        k_tree_pad<<<tree_grid(2 * K), 256, 0, st>>>(T, child, K, j);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(T, T, j + 1, root, 0, (size_t)(K >> j), st)) != SA_OK) return rc;
+        k_tree_pairmul<<<tree_grid(K), 256, 0, st>>>(parent, T, K, j);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(parent, parent, j + 1, root, 1, (size_t)(K >> (j + 1)), st)) != SA_OK) return rc;
+        k_tree_fix<<<tree_grid(K / 2), 256, 0, st>>>(parent, child, K, j, t.k, 0);
+        SA_LAUNCH_CHECK();
+    }
+    return SA_OK;
+}
+static int tree_alloc(PolyTree &t, size_t k, bool keep_transforms, size_t extra_elems, fe **extra, cudaStream_t st) {
+    t.k = (long long)k;
+    t.logK = 0;
+    while ((size_t(1) << t.logK) < k) t.logK++;
+    if (t.logK > TREE_MAX_LOG) return SA_ESIZE;
+    t.K = 1ll << t.logK;
+    const size_t K = (size_t)t.K;
+    const size_t lv = (size_t)(t.logK + 1) * K, tr = keep_transforms ? (size_t)t.logK * 2 * K : 0, sc = 2 * K;
+    fe *ws = nullptr;
+    int rc = get_workspace((void **)&ws, sizeof(fe) * (lv + tr + sc + extra_elems), st, 8);
+    if (rc != SA_OK) return rc;
+    t.levels = ws;
+    t.transforms = keep_transforms ? ws + lv : nullptr;
+    t.scratch = ws + lv + tr;
+    if (extra) *extra = ws + lv + tr + sc;
+    return SA_OK;
+}
+
+extern "C" {
+
 int sa_zerofier(void *out, const void *domain, size_t k, void *stream) {
-    if (k > (size_t)ZF_MAXK) return SA_ESIZE;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(fe) * (2 * k + 1);
-    {
+    tree_config();
+    if (k == 0) {  // the empty product (the drop-in answers Polynomial([]) before it gets here, ntt.py:70-71)
+        const fe one = fe_one();
+        SA_CUDA(cudaMemcpyAsync(out, &one, sizeof(fe), cudaMemcpyHostToDevice, st));
+        SA_CUDA(cudaStreamSynchronize(st));
+        return SA_OK;
+    }
+    if (k <= (size_t)g_zf_direct_max && k <= (size_t)ZF_MAXK) {
+        const size_t smem = sizeof(fe) * (2 * k + 1);
         static std::atomic<bool> attr_done[SA_MAX_DEVICES];
         const int rc = optin_smem(k_zerofier, attr_done, sizeof(fe) * (2 * ZF_MAXK + 1));
         if (rc != SA_OK) return rc;
+        k_zerofier<<<1, ZF_THREADS, smem, st>>>((fe *)out, (const fe *)domain, (int)k);
+        SA_LAUNCH_CHECK();
+        return SA_OK;
     }
-    k_zerofier<<<1, ZF_THREADS, smem, st>>>((fe *)out, (const fe *)domain, (int)k);
+    PolyTree t;
+    int rc = tree_alloc(t, k, false, 0, nullptr, st);
+    if (rc != SA_OK) return rc;
+    if ((rc = tree_build(t, (const fe *)domain, st)) != SA_OK) return rc;
+    k_tree_root<<<(unsigned)((k + 1 + 255) / 256), 256, 0, st>>>((fe *)out, t.levels + (size_t)t.logK * t.K, t.k, t.K);
     SA_LAUNCH_CHECK();
     return SA_OK;
 }
 
-int sa_interpolate(void *out, const void *domain, const void *values, size_t k, void *stream) {
-    if (k == 0) return SA_OK;
-    if (k > 2 * (size_t)ZF_MAXK) return SA_ESIZE;
-    cudaStream_t st = (cudaStream_t)stream;
+static int interpolate_direct(void *out, const void *domain, const void *values, size_t k, cudaStream_t st) {
     // workspace: z (k+1) | w (k) | flag | QT (k*k)
     char *ws = nullptr;
     const size_t z_off = 0, w_off = sizeof(fe) * (k + 1), f_off = w_off + sizeof(fe) * k,
@@ -1118,11 +1284,7 @@ int sa_interpolate(void *out, const void *domain, const void *values, size_t k, 
     if (rc != SA_OK) return rc;
     fe *z = (fe *)(ws + z_off), *w = (fe *)(ws + w_off), *QT = (fe *)(ws + q_off);
     int *flag = (int *)(ws + f_off);
-    if (k <= (size_t)ZF_MAXK) {
-        if ((rc = sa_zerofier(z, domain, k, stream)) != SA_OK) return rc;
-    } else {  // two halves multiplied on the host side is the caller's job (ntt.py recursion)
-        return SA_ESIZE;
-    }
+    if ((rc = sa_zerofier(z, domain, k, (void *)st)) != SA_OK) return rc;
     SA_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     const int bs = 128, grid = (int)((k + bs - 1) / bs);
     k_interp_weights<<<grid, bs, 0, st>>>(w, (const fe *)domain, (const fe *)values, z, (int)k, flag);
@@ -1135,6 +1297,59 @@ int sa_interpolate(void *out, const void *domain, const void *values, size_t k, 
     SA_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     SA_CUDA(cudaStreamSynchronize(st));
     return h ? SA_EDIVZERO : SA_OK;
+}
+
+// Lagrange interpolation through the subproduct tree, everything on the device:
+//   M = prod (X - d_i) (tree), q_i = v_i / M'(d_i), and the interpolant sum_i q_i M / (X - d_i) is
+//   combined bottom-up: P_node = P_L * M_R + P_R * M_L (the M's are the tree's nodes, their transforms
+//   kept from the build).  M'(d_i) comes from one Horner kernel (k^2 / 2 multiply-adds, all points in
+//   parallel); coinciding points give M'(d_i) = 0 -> SA_EDIVZERO like the division at ntt.py:124-125.
+static int interpolate_tree(void *out, const void *domain, const void *values, size_t k, cudaStream_t st) {
+    PolyTree t;
+    fe *extra = nullptr;
+    // extra: z (K + 1) | dz (K) | ev (K) | q (K) | P levels ping-pong (2 * K)
+    const size_t Kpad = (size_t)1 << (k <= 1 ? 0 : (64 - __builtin_clzll((unsigned long long)(k - 1))));
+    int rc = tree_alloc(t, k, true, 6 * Kpad + 16, &extra, st);
+    if (rc != SA_OK) return rc;
+    const size_t K = (size_t)t.K;
+    fe *z = extra, *dz = z + K + 1, *ev = dz + K, *q = ev + K, *Pa = q + K, *Pb = Pa + K;
+    if ((rc = tree_build(t, (const fe *)domain, st)) != SA_OK) return rc;
+    k_tree_root<<<(unsigned)((k + 1 + 255) / 256), 256, 0, st>>>(z, t.levels + (size_t)t.logK * K, t.k, t.K);
+    SA_LAUNCH_CHECK();
+    k_derivative<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(dz, z, (long long)k);
+    SA_LAUNCH_CHECK();
+    if ((rc = sa_poly_eval(ev, dz, k, domain, k, (void *)st)) != SA_OK) return rc;
+    if ((rc = sa_pointwise_div(q, values, ev, k, (void *)st)) != SA_OK) return rc;  // SA_EDIVZERO: repeated point
+    k_tree_qleaves<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(Pa, q, t.k, t.K);
+    SA_LAUNCH_CHECK();
+    fe *cur = Pa, *nxt = Pb;
+    for (int j = 0; j < t.logK; j++) {
+        uint64_t root[2];
+        tree_root_of_unity(root, j + 1);
+        const fe *VT = t.transforms + (size_t)j * 2 * K;
+        k_tree_pad<<<tree_grid(2 * (long long)K), 256, 0, st>>>(t.scratch, cur, t.K, j);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(t.scratch, t.scratch, j + 1, root, 0, K >> j, (void *)st)) != SA_OK) return rc;
+        k_tree_cross<<<tree_grid((long long)K), 256, 0, st>>>(nxt, t.scratch, VT, t.K, j);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(nxt, nxt, j + 1, root, 1, K >> (j + 1), (void *)st)) != SA_OK) return rc;
+        k_tree_fix<<<tree_grid((long long)K / 2), 256, 0, st>>>(nxt, cur, t.K, j, t.k, 1);
+        SA_LAUNCH_CHECK();
+        fe *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    SA_CUDA(cudaMemcpyAsync(out, cur, sizeof(fe) * k, cudaMemcpyDeviceToDevice, st));
+    return SA_OK;
+}
+
+int sa_interpolate(void *out, const void *domain, const void *values, size_t k, void *stream) {
+    if (k == 0) return SA_OK;
+    tree_config();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k <= (size_t)g_interp_direct_max && k <= (size_t)ZF_MAXK) return interpolate_direct(out, domain, values, k, st);
+    if (k > ((size_t)1 << TREE_MAX_LOG)) return SA_ESIZE;
+    return interpolate_tree(out, domain, values, k, st);
 }
 
 // ---- Merkle / FRI ----

@@ -205,7 +205,7 @@ class CudaEngine:
                                           points.shape[0], self._stream()))
         return out
 
-    MAX_DIRECT_POINTS = 4096  # sa_zerofier / sa_interpolate handle this many points per call
+    MAX_DIRECT_POINTS = 1 << 20  # sa_zerofier / sa_interpolate handle this many points per call
 
     def zerofier(self, domain):
         domain = domain.contiguous()

@@ -86,7 +86,7 @@ class OracleEngine:
         self._log("poly_eval", coeffs.shape[0], points.shape[0])
         return O.poly_eval_np(coeffs, points)
 
-    MAX_DIRECT_POINTS = 4096
+    MAX_DIRECT_POINTS = 1 << 20
 
     def zerofier(self, domain):
         self._log("zerofier", domain.shape[0])

@@ -405,16 +405,18 @@ def test_elementwise_ops(eng):
     assert (down(eng, eng.poly_eval(up(eng, coeffs), up(eng, pts))) == O.poly_eval_np(coeffs, pts)).all()
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 17, 284, 1000, 4096])
+@pytest.mark.parametrize("k", [1, 2, 3, 17, 284, 512, 513, 1000, 1024, 1025, 1500, 2048, 4096, 5000])
 def test_zerofier_and_interpolate(eng, k):
+    """sa_zerofier / sa_interpolate vs the oracle: the one-CTA / k x k kernels (k <= 512 / 1024) and the
+    device subproduct tree above them (full and ragged trees: 513, 1025, 1500, 5000 points)"""
     dom = rand_np(70 + k, k)
     vals = rand_np(71 + k, k)
     z = down(eng, eng.zerofier(up(eng, dom)))
-    assert (z == O.zerofier_np(dom)).all()
-    if k <= 1000:
+    assert z.shape[0] == k + 1 and (z == O.zerofier_np(dom)).all()
+    if k <= 1500:
         got = down(eng, eng.interpolate(up(eng, dom), up(eng, vals)))
-        assert (got == O.interpolate_np(dom, vals)).all()
-    else:  # full size: property check, the interpolant takes the prescribed values
+        assert got.shape[0] == k and (got == O.interpolate_np(dom, vals)).all()
+    else:  # property check, the interpolant takes the prescribed values
         poly = eng.interpolate(up(eng, dom), up(eng, vals))
         assert (down(eng, eng.poly_eval(poly, up(eng, dom))) == vals).all()
         assert (down(eng, eng.poly_eval(up(eng, z), up(eng, dom))) == 0).all()
@@ -422,6 +424,33 @@ def test_zerofier_and_interpolate(eng, k):
         dom[k - 1] = dom[0]
         with pytest.raises(AssertionError, match="divide by zero"):
             eng.interpolate(up(eng, dom), up(eng, vals))
+
+
+@pytest.mark.parametrize("k", [1 << 16, (1 << 16) + 12345, 1 << 18])
+def test_zerofier_and_interpolate_large_by_property(eng, k):
+    """one C call each at sizes the oracle's O(k^2) loops cannot reach: the zerofier is monic, vanishes on
+    the domain, equals the product of the zerofiers of the two halves (fast_multiply, ntt.py:76-80); the
+    interpolant has degree < k and takes the prescribed values (Horner kernel on the device)"""
+    dom = rand_np(170 + k % 97, k)
+    vals = rand_np(171 + k % 97, k)
+    vd = up(eng, dom)
+    z = eng.zerofier(vd)
+    zh = down(eng, z)
+    assert zh.shape[0] == k + 1 and (zh[k] == np.array([1, 0], dtype=np.uint64)).all()
+    sample = vd if k <= 1 << 16 else vd[::37].contiguous()
+    assert (down(eng, eng.poly_eval(z, sample)) == 0).all()
+    half = k // 2
+    zl, zr = eng.zerofier(vd[:half].contiguous()), eng.zerofier(vd[half:].contiguous())
+    log_n = k.bit_length() + 1  # > deg(zl * zr)
+    n = 1 << log_n
+    w = O.primitive_nth_root(n)
+    prod = eng.ntt(eng.pointwise_mul(eng.ntt(eng.pad(zl, n), log_n, w), eng.ntt(eng.pad(zr, n), log_n, w)), log_n, w,
+                   inverse=True)
+    assert (down(eng, prod)[:k + 1] == zh).all() and (down(eng, prod)[k + 1:] == 0).all()
+    if k <= (1 << 16) + 12345:
+        poly = eng.interpolate(vd, up(eng, vals))
+        assert eng.length(poly) == k
+        assert (down(eng, eng.poly_eval(poly, vd)) == vals).all()
 
 
 @pytest.mark.parametrize("log_n", [0, 1, 2, 5, 6, 7, 9, 10, 11, 13, 14, 15, 16, 17, 18])
