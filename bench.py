@@ -327,6 +327,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     single_us = ev2.elapsed_time(ev3) / reps * 1e3
 
+    if os.environ.get("SA_BENCH_QUICK") == "1":  # kernel experiments (tools/gpu_*.sh): transform timings only
+        if rank == 0:
+            os.write(json_fd, (json.dumps({"quick": True, "ms_per_step": ms_per_step, "value": value,
+                                           "single_ntt_us": single_us, "int_peak": int_peak,
+                                           "lib": os.environ.get("SA_B200_LIB"),
+                                           "env": {k: v for k, v in os.environ.items() if k.startswith("SA_NTT")}}) + "\n").encode())
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---- e2e: the same step through the C-ABI host entry (pinned host buffers, H2D + D2H inside)
     # The host buffers come from the library's own allocator (sa_host_alloc: page-locked, placed on the NUMA
     # node of this rank's GPU, so eight ranks do not push half of their copies across the socket interconnect).

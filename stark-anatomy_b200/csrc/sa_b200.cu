@@ -88,13 +88,20 @@ __global__ void __launch_bounds__(TilePlan<LOGL, ELOG, C>::THREADS, TileLaunch<L
     fe *sm = smem + (size_t)tic * P::L * C;
     fe *tw = nullptr;
     uint64_t *bar = nullptr;
+    // programmatic dependent launch: the next launch on this stream (pass 2 after pass 1, the next transform
+    // of a chain) may become resident while this grid still runs; it parks at griddepcontrol.wait below
+    asm volatile("griddepcontrol.launch_dependents;");
     if constexpr (P::NLOOP > 0) {
-        // stage the twiddle table of this tile length into shared memory (bulk-async copy + mbarrier)
+        // stage the twiddle table of this tile length into shared memory (bulk-async copy + mbarrier);
+        // the table is a cached constant of the plan, not an output of the preceding launch
         tw = smem + P::TILE_BYTES / sizeof(fe);
         bar = reinterpret_cast<uint64_t *>(tw + P::L);
         if (threadIdx.x == 0) tile_stage_twiddles(tw, a.tw, (uint32_t)P::TW_BYTES, bar);
         __syncthreads();  // the barrier is initialised before anybody polls it
     }
+    // everything the preceding launch wrote (the intermediate of the four-step split, or this call's input)
+    // is complete and visible after this point; a no-op for a launch without the PDL attribute
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll 1
     for (int st = 0; st < P::NLOOP; st++) {
         S::full(st, t, sm, a, b, col0, valid, tw, bar);
@@ -784,6 +791,23 @@ static int launch_tile_variant(const TileArgs &a, cudaStream_t st) {
         static std::atomic<bool> attr_done[SA_MAX_DEVICES];
         const int rc = optin_smem(ntt_tile_kernel<LOGL, ELOG, C, FLAGS>, attr_done, smem);
         if (rc != SA_OK) return rc;
+    }
+    static const bool pdl = !(getenv("SA_NTT_PDL") && atoi(getenv("SA_NTT_PDL")) == 0);
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(P::THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int tpb = tiles_per_batch;
+        SA_CUDA(cudaLaunchKernelEx(&cfg, ntt_tile_kernel<LOGL, ELOG, C, FLAGS>, a, total, tpb));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return SA_OK;
     }
     ntt_tile_kernel<LOGL, ELOG, C, FLAGS><<<(unsigned)grid, P::THREADS, smem, st>>>(a, total, tiles_per_batch);
     SA_LAUNCH_CHECK();
