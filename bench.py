@@ -104,9 +104,23 @@ def cpu_arm(steps, warmup, batch):
     x = np.stack([rng.integers(0, 1 << 64, size=(batch, N), dtype=np.uint64),
                   rng.integers(0, 0xCB80000000000000, size=(batch, N), dtype=np.uint64)], axis=2)
     w = O.primitive_nth_root(N)
-    O.lib().so_set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use the whole host
+    # torchrun exports OMP_NUM_THREADS=1: size the team ourselves.  The port is a cache-hostile recursion, so
+    # more threads are not always faster on a two-socket host: one probe step per candidate team size, the
+    # fastest one is used and reported as `cores` (every thread of that team works: transforms, recursion and
+    # combine loops are OpenMP tasks)
+    ncpu = os.cpu_count() or 1
+    best = None
+    for cand in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, batch)}, reverse=True):
+        O.lib().so_set_threads(cand)
+        O.ntt_batch_np(w, x[:min(batch, 4)])  # team start-up
+        t0 = time.perf_counter()
+        O.ntt_batch_np(w, x)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, cand)
+    O.lib().so_set_threads(best[1])
     threads = O.lib().so_num_threads()
-    for _ in range(warmup):
+    for _ in range(max(warmup - 1, 0)):
         O.ntt_batch_np(w, x)
     t0 = time.perf_counter()
     for _ in range(steps):

@@ -368,10 +368,11 @@ __device__ __forceinline__ void merkle_publish_root(const MerkleArgs &a, const u
     __threadfence_system();
     out[8] = a.root_seq;
 }
-__global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
-    __shared__ uint64_t sm[MK_THREADS * 8];
+// the work of one CTA (`blk` of `nblocks`) on one level-range of one tree; sm = MK_THREADS * 8 words of
+// shared memory.  Called once per launch by k_merkle_chunk and once per round by k_fri_tail.
+__device__ __forceinline__ void merkle_chunk_body(const MerkleArgs &a, const long long blk, const unsigned nblocks,
+                                                  uint64_t *sm) {
     const int tid = threadIdx.x;
-    const long long blk = blockIdx.x;
     const int active = a.chunk >> a.ipt_log;  // threads with a private subtree
     uint64_t d[8];
     if (tid < active) merkle_private(d, a, blk, tid);
@@ -419,16 +420,16 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
             __syncthreads();
         }
         if (pass == 1 || a.ticket == nullptr) break;
-        // Every CTA has reduced its chunk to one digest (heap node gridDim.x + blk).  The CTA that
-        // arrives last reduces those gridDim.x digests as well instead of leaving them to one more
+        // Every CTA has reduced its chunk to one digest (heap node nblocks + blk).  The CTA that
+        // arrives last reduces those nblocks digests as well instead of leaving them to one more
         // launch (each thread fences its own stores, the barrier orders them before the ticket).
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+        if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == nblocks - 1;
         __syncthreads();
         if (!s_last) return;
-        const int g = (int)gridDim.x;
+        const int g = (int)nblocks;
         if (tid == 0) *a.ticket = 0;  // as the next launch on this stream expects it
         __threadfence();
         if (tid < g) {
@@ -443,6 +444,90 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_consta
         coop_max = MK_THREADS / 4;  // this part is a dependency chain whatever the shape below was
     }
     if (a.root_out && tid == 0) merkle_publish_root(a, sm);
+}
+
+__global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
+    __shared__ uint64_t sm[MK_THREADS * 8];
+    merkle_chunk_body(a, blockIdx.x, gridDim.x, sm);
+}
+
+// Persistent tail of Fri.commit (FriTailArgs, fri_merkle.cuh): every round is the fused fold + leaf hash +
+// tree of k_merkle_chunk mode 2 with the last-CTA top reduction; between rounds the CTAs that still have
+// work wait for the next challenge.  Grid = the CTAs of the first (widest) tail round, all co-resident.
+__device__ __forceinline__ bool fri_tail_spin(volatile const unsigned long long *flag, unsigned long long want,
+                                              long long limit, volatile const uint64_t *abort_flag) {
+    const long long t0 = clock64();
+    while (*flag < want) {
+        if (abort_flag && *abort_flag != 0) return false;
+        if (clock64() - t0 > limit) return false;
+    }
+    return true;
+}
+__global__ void __launch_bounds__(MK_THREADS) k_fri_tail(const __grid_constant__ FriTailArgs t) {
+    __shared__ uint64_t sm[MK_THREADS * 8];
+    __shared__ uint32_t s_sm[4];
+    __shared__ int s_ok;
+    const int tid = threadIdx.x;
+    const long long blk = blockIdx.x;
+    fe s_m = t.s_m0;
+    for (int i = 0; i < t.nrounds; i++) {
+        MerkleArgs a;
+        a.width = t.width0 >> i;
+        a.mode = 2;
+        merkle_shape(a);
+        const unsigned nblocks = (unsigned)(a.width / a.chunk);
+        if (blk >= nblocks) return;  // the rounds only get narrower: nothing left for this CTA
+        if (i > 0) {
+            // the challenge of this round: CTA 0 takes it from the host page and forwards it, the others
+            // watch the device flag (L2) instead of all polling across PCIe
+            if (tid == 0) {
+                const unsigned long long want = t.seq0 + (unsigned long long)i - 1;
+                volatile unsigned long long *bc = (volatile unsigned long long *)t.bcast;
+                bool ok;
+                if (blk == 0) {
+                    ok = fri_tail_spin((volatile const unsigned long long *)(t.host + 18), want, t.spin_limit, t.host + 19);
+                    if (ok) {
+                        __threadfence_system();
+                        const uint64_t lo = t.host[16], hi = t.host[17];
+                        bc[2] = lo;
+                        bc[3] = hi;
+                        __threadfence();
+                        bc[0] = want;
+                    } else {
+                        bc[1] = 1;                             // tell the others to give up as well
+                        __threadfence();
+                        if (t.host[19] == 0) t.host[20] = 1;  // (a timeout, not a host abort)
+                    }
+                } else {
+                    ok = fri_tail_spin(bc, want, t.spin_limit, (volatile const uint64_t *)(bc + 1));
+                }
+                if (ok) {
+                    __threadfence();
+                    const uint64_t lo = bc[2], hi = bc[3];
+                    s_sm[0] = (uint32_t)lo;
+                    s_sm[1] = (uint32_t)(lo >> 32);
+                    s_sm[2] = (uint32_t)hi;
+                    s_sm[3] = (uint32_t)(hi >> 32);
+                }
+                s_ok = ok ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_ok) return;
+            s_m = fe_make(s_sm[0], s_sm[1], s_sm[2], s_sm[3]);
+        }
+        a.tree = t.tree[i];
+        a.values = nullptr;
+        a.prev = i == 0 ? t.prev0 : t.layer[i - 1];
+        a.next = t.layer[i];
+        a.xinv = t.xinv[i];
+        a.s_m = s_m;
+        a.inv2_m = t.inv2_m;
+        a.ticket = nblocks > 1 ? t.ticket : nullptr;
+        a.root_out = const_cast<uint64_t *>(t.host);
+        a.root_seq = t.seq0 + (unsigned long long)i;
+        merkle_chunk_body(a, blk, nblocks, sm);
+        __syncthreads();  // sm and s_sm are reused by the next round
+    }
 }
 
 __global__ void k_merkle_paths(uint64_t *out, const uint64_t *tree, long long n, int depth,
@@ -1573,18 +1658,75 @@ static int wait_for_root(uint64_t *root_host, unsigned long long seq, cudaStream
     return SA_OK;
 }
 
+}  // extern "C"
+
+// ---- can the host talk to a RUNNING kernel?  (the persistent FRI tail depends on it) ----
+// Under tools that serialise launches (ncu / compute-sanitizer make a launch return only when the kernel has
+// finished; CUDA_LAUNCH_BLOCKING=1 does the same) a kernel that waits for the host would wait for ever, so the
+// tail is only used after this probe has passed once in the process: a one-thread kernel waits (at most
+// ~50 ms) for a flag the host sets right AFTER the launch call has returned.
+__global__ void k_host_probe(volatile uint64_t *page, long long limit) {
+    const long long t0 = clock64();
+    while (page[0] == 0 && clock64() - t0 < limit) {
+    }
+    page[1] = page[0] != 0 ? 1 : 2;
+    __threadfence_system();
+}
+static int g_tail_mode = -1;  // -1 not probed yet, 0 per-round launches, 1 persistent tail
+static std::mutex g_tail_mu;
+static bool fri_tail_allowed(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_tail_mu);
+    if (g_tail_mode >= 0) return g_tail_mode == 1;
+    g_tail_mode = 0;
+    if (const char *e = getenv("SA_FRI_PERSISTENT"))
+        if (atoi(e) == 0) return false;
+    uint64_t *page = nullptr, *page_dev = nullptr;
+    if (cudaHostAlloc((void **)&page, 64, cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    page[0] = page[1] = 0;
+    bool ok = cudaHostGetDevicePointer((void **)&page_dev, page, 0) == cudaSuccess;
+    if (ok) {
+        k_host_probe<<<1, 1, 0, st>>>(page_dev, 100000000ll);
+        __atomic_store_n(&page[0], 1ull, __ATOMIC_RELEASE);  // only reaches a kernel that is running NOW
+        ok = cudaStreamSynchronize(st) == cudaSuccess && page[1] == 1;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    cudaFreeHost(page);
+    cudaGetLastError();
+    g_tail_mode = ok ? 1 : 0;
+    return ok;
+}
+// per (device, stream): ticket-like broadcast words of the tail kernel
+static std::map<std::pair<int, cudaStream_t>, unsigned long long *> g_bcast;
+static unsigned long long *get_bcast(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    auto &slot = g_bcast[std::make_pair(dev, st)];
+    if (!slot && cudaMalloc((void **)&slot, 256) != cudaSuccess) {
+        slot = nullptr;
+        cudaGetLastError();
+    }
+    return slot;
+}
+
+extern "C" {
+
 int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int rounds,
                   const uint64_t offset[2], const uint64_t omega[2], sa_fri_challenge_fn challenge, void *user,
                   void *stream) {
     if (!host_is_pow2(n) || rounds < 1 || (n >> (rounds - 1)) < 1) return SA_ESIZE;
     cudaStream_t st = (cudaStream_t)stream;
-    // landing pad of the per-round root (8 words) + sequence number, written by the kernel itself
+    // landing pad of the per-round root (8 words) + sequence number, written by the kernel itself; words
+    // 16.. carry the challenge the other way for the persistent tail (FriTailArgs::host)
     static thread_local uint64_t *root_pinned = nullptr;
     static thread_local uint64_t *root_dev = nullptr;  // the same memory as the device addresses it
     static thread_local unsigned long long root_seq = 0;
     if (!root_pinned) {
-        SA_CUDA(cudaHostAlloc((void **)&root_pinned, 128, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(root_pinned, 0, 128);
+        SA_CUDA(cudaHostAlloc((void **)&root_pinned, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(root_pinned, 0, 256);
     }
     SA_CUDA(cudaHostGetDevicePointer((void **)&root_dev, root_pinned, 0));  // per current device
     fe off = fe_from_limbs(offset), om = fe_from_limbs(omega);
@@ -1600,6 +1742,41 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
     static const bool trace = getenv("SA_FRI_TRACE") != nullptr;  // per-round host timeline on stderr
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
+    // The narrow rounds (<= 2^FRI_TAIL_MAX_LOG leaves) run in ONE persistent launch when the host can talk to
+    // a running kernel; their x^-1 tables are fetched up front (building one synchronises the stream).
+    int tail_from = rounds;  // first round r (>= 1) whose tree has n >> r <= 2^FRI_TAIL_MAX_LOG leaves
+    for (int r = 1; r < rounds; r++)
+        if ((n >> r) <= ((size_t)1 << FRI_TAIL_MAX_LOG)) {
+            tail_from = r;
+            break;
+        }
+    std::vector<XinvPtr> tail_xinv;
+    unsigned int *tail_ticket = nullptr;
+    unsigned long long *tail_bcast = nullptr;
+    if (tail_from < rounds && rounds - tail_from <= FRI_TAIL_MAX_ROUNDS && fri_tail_allowed(st)) {
+        fe om_r = om;
+        for (int r = 1; r < rounds; r++) {  // round r folds with omega^(2^(r-1)) over n >> (r-1) points
+            if (r >= tail_from) {
+                XinvPtr x;
+                if ((rc = get_xinv(&x, om_r, n >> (r - 1), st)) != SA_OK) return rc;
+                tail_xinv.push_back(x);
+            }
+            om_r = fe_montmul(fe_to_mont(om_r), om_r);
+        }
+        tail_ticket = get_ticket(st);
+        tail_bcast = get_bcast(st);
+        if (!tail_ticket || !tail_bcast) tail_xinv.clear();
+    }
+    const bool use_tail = !tail_xinv.empty();
+    bool tail_running = false;
+    unsigned long long tail_seq0 = 0;
+    auto abort_tail = [&]() {
+        if (tail_running) {
+            __atomic_store_n(&root_pinned[19], 1ull, __ATOMIC_RELEASE);
+            cudaStreamSynchronize(st);
+            root_pinned[19] = 0;
+        }
+    };
     for (int r = 0; r < rounds; r++) {
         if (r == 0) {
             MerkleArgs a;
@@ -1611,33 +1788,89 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
             if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
         }
         const double t_launched = now();
-        if ((rc = wait_for_root(root_pinned, root_seq, st)) != SA_OK) return rc;
+        if ((rc = wait_for_root(root_pinned, root_seq, st)) != SA_OK) {
+            if (tail_running && root_pinned[20] != 0) g_last_error = "sa_fri_commit: the tail kernel timed out waiting for a challenge";
+            return rc;
+        }
         const double t_synced = now();
         uint64_t alpha[2] = {0, 0};
         const int want = r != rounds - 1;
-        if (challenge(user, r, (const uint8_t *)root_pinned, alpha, want) != 0) return SA_ECALLBACK;
+        if (challenge(user, r, (const uint8_t *)root_pinned, alpha, want) != 0) {
+            abort_tail();
+            return SA_ECALLBACK;
+        }
         if (trace) {
             const double t_cb = now();
-            fprintf(stderr, "sa_fri_commit round %2d len %8zu: launch %.1f us, wait %.1f us, callback %.1f us\n", r, len,
-                    t_launched - t_mark, t_synced - t_launched, t_cb - t_synced);
+            fprintf(stderr, "sa_fri_commit round %2d len %8zu: launch %.1f us, wait %.1f us, callback %.1f us%s\n", r, len,
+                    t_launched - t_mark, t_synced - t_launched, t_cb - t_synced, tail_running ? " (tail kernel)" : "");
             t_mark = t_cb;
         }
         if (!want) break;
-        // fold layer r into layer r+1 and build its tree, one fused kernel (+ upper-level launches)
-        XinvPtr xinv;
-        if ((rc = get_xinv(&xinv, om, len, st)) != SA_OK) return rc;
+        // fold layer r into layer r+1 and build its tree: alpha / (2 offset), Montgomery form
+        const fe s_m = fe_montmul(fe_montmul(fe_to_mont(fe_from_limbs(alpha)), inv2_m), oinv_m);
         uint8_t *next_tree = tree + 128 * len;  // this tree has 2 * len nodes of 64 bytes
-        MerkleArgs a;
-        memset(&a, 0, sizeof(a));
-        a.tree = (uint64_t *)next_tree;
-        a.width = (long long)(len / 2);
-        a.mode = 2;
-        a.prev = cur;
-        a.next = layer_out;
-        a.xinv = xinv->tab;
-        a.inv2_m = inv2_m;
-        a.s_m = fe_montmul(fe_montmul(fe_to_mont(fe_from_limbs(alpha)), inv2_m), oinv_m);  // alpha / (2 offset)
-        if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
+        if (tail_running) {
+            // the kernel is waiting for exactly this: s_m, then its sequence number (release order)
+            root_pinned[16] = (uint64_t)s_m.v[0] | ((uint64_t)s_m.v[1] << 32);
+            root_pinned[17] = (uint64_t)s_m.v[2] | ((uint64_t)s_m.v[3] << 32);
+            __atomic_store_n(&root_pinned[18], tail_seq0 + (unsigned long long)(r + 1 - tail_from) - 1, __ATOMIC_RELEASE);
+            ++root_seq;
+        } else if (use_tail && r + 1 == tail_from) {
+            FriTailArgs t;
+            memset(&t, 0, sizeof(t));
+            t.nrounds = rounds - tail_from;
+            t.width0 = (long long)(len / 2);
+            t.prev0 = cur;
+            fe *lo = layer_out;
+            uint8_t *tr = next_tree;
+            for (int i = 0; i < t.nrounds; i++) {
+                const size_t w = (len / 2) >> i;
+                t.layer[i] = lo;
+                t.tree[i] = (uint64_t *)tr;
+                t.xinv[i] = tail_xinv[i]->tab;
+                lo += w;
+                tr += 128 * w;
+            }
+            t.inv2_m = inv2_m;
+            t.s_m0 = s_m;
+            t.ticket = tail_ticket;
+            t.bcast = tail_bcast;
+            t.host = root_dev;
+            tail_seq0 = root_seq + 1;
+            t.seq0 = tail_seq0;
+            static const long long limit_ticks = [] {
+                const char *e = getenv("SA_FRI_TAIL_TIMEOUT_S");
+                const double sec = e ? atof(e) : 20.0;
+                return (long long)(sec * 2.0e9);
+            }();
+            t.spin_limit = limit_ticks;
+            root_pinned[19] = root_pinned[20] = 0;
+            SA_CUDA(cudaMemsetAsync(tail_bcast, 0, 64, st));
+            MerkleArgs shape;
+            shape.width = t.width0;
+            shape.mode = 2;
+            merkle_shape(shape);
+            const unsigned grid = (unsigned)(t.width0 / shape.chunk);
+            if (grid > (unsigned)FRI_TAIL_MAX_CTAS) return SA_ESIZE;  // (cannot happen: widths <= 2^16)
+            k_fri_tail<<<grid, MK_THREADS, 0, st>>>(t);
+            SA_LAUNCH_CHECK();
+            tail_running = true;
+            ++root_seq;
+        } else {
+            XinvPtr xinv;
+            if ((rc = get_xinv(&xinv, om, len, st)) != SA_OK) return rc;
+            MerkleArgs a;
+            memset(&a, 0, sizeof(a));
+            a.tree = (uint64_t *)next_tree;
+            a.width = (long long)(len / 2);
+            a.mode = 2;
+            a.prev = cur;
+            a.next = layer_out;
+            a.xinv = xinv->tab;
+            a.inv2_m = inv2_m;
+            a.s_m = s_m;
+            if ((rc = merkle_reduce(a, st, root_dev, ++root_seq)) != SA_OK) return rc;
+        }
         cur = layer_out;
         layer_out += len / 2;
         tree = next_tree;
@@ -1648,6 +1881,11 @@ int sa_fri_commit(void *layers, void *trees, const void *codeword, size_t n, int
         oinv_m = fe_montmul(oinv_m, oinv_m);  // (offset^2)^-1, stays in Montgomery form
     }
     return SA_OK;
+}
+
+int sa_fri_tail_mode(void) {
+    std::lock_guard<std::mutex> lock(g_tail_mu);
+    return g_tail_mode;
 }
 
 size_t sa_cache_limit(size_t bytes) {
