@@ -130,20 +130,32 @@ def cpu_arm(steps, warmup, batch):
 
 
 def cpu_fri_commit(reps=2):
-    """the CPU oracle port of Fri.commit (fri.py:56-96) on the seed-1 2^20 codeword, all host threads;
-    returns (ms per commit, roots)"""
+    """the CPU oracle port of Fri.commit (fri.py:56-96) on the seed-1 2^20 codeword; the OpenMP team size is
+    probed upwards from 8 threads and the fastest one is used (on the two-socket GPU hosts the whole machine is
+    SLOWER than one socket's worth of threads on the narrow tree levels); returns (ms per commit, roots, threads)"""
     import numpy as np
     import oracle as O
     rng = np.random.default_rng(1)
     cw = np.stack([rng.integers(0, 1 << 64, size=N, dtype=np.uint64),
                    rng.integers(0, 0xCB80000000000000, size=N, dtype=np.uint64)], axis=1)
-    O.lib().so_set_threads(os.cpu_count() or 1)
     w = O.primitive_nth_root(N)
-    O.fri_commit_np(cw, O.GENERATOR, w, 4, 64)
+    ncpu = os.cpu_count() or 1
+    best = None
+    for cand in sorted({c for c in (8, 16, 32, 64, 128, ncpu) if c <= ncpu} or {ncpu}):
+        O.lib().so_set_threads(cand)
+        O.merkle_root_np(cw[:1 << 12])  # team start-up
+        t0 = time.perf_counter()
+        O.fri_commit_np(cw, O.GENERATOR, w, 4, 64)
+        dt = time.perf_counter() - t0
+        if best is not None and dt > 1.3 * best[0]:
+            break  # getting worse: larger teams are not tried
+        if best is None or dt < best[0]:
+            best = (dt, cand)
+    O.lib().so_set_threads(best[1])
     t0 = time.perf_counter()
     for _ in range(reps):
         roots, _, _ = O.fri_commit_np(cw, O.GENERATOR, w, 4, 64)
-    return (time.perf_counter() - t0) / reps * 1e3, roots
+    return (time.perf_counter() - t0) / reps * 1e3, roots, best[1]
 
 
 def run_reference(args):
@@ -153,7 +165,7 @@ def run_reference(args):
     import __graft_entry__ as G
     G.build_oracle()
     value, threads, dt = cpu_arm(args.steps, args.warmup, BATCH)
-    fri_ms, _ = cpu_fri_commit()
+    fri_ms, _, fri_threads = cpu_fri_commit()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -169,8 +181,9 @@ def run_reference(args):
         # second half of BASELINE.json's metric, same arm: Fri.commit of a 2^20 codeword (12 rounds,
         # 4 193 268 blake2b compressions) on the CPU port, all threads
         "fri_commit_ms_2_20": fri_ms,
-        "fri_commit": {"ms": fri_ms, "cores": threads, "kind": "port", "compressions_per_s": FRI_COMPRESSIONS / (fri_ms * 1e-3),
-                       "sample": "2 commits, oracle so_merkle_tree / so_fri_fold (OpenMP); the reference's own "
+        "fri_commit": {"ms": fri_ms, "cores": fri_threads, "kind": "port", "compressions_per_s": FRI_COMPRESSIONS / (fri_ms * 1e-3),
+                       "sample": "2 commits, oracle so_merkle_tree / so_fri_fold (OpenMP, fastest team size of 8..all "
+                                 "threads); the reference's own "
                                  "Fri.commit takes 73 100 ms on one core (BASELINE.md section 2)"},
     }
     print(json.dumps(line))
@@ -413,9 +426,10 @@ def run_ours(args):
             fri_commit(constant=True)  # the same ladder without the pickle + shake_256 of the challenge
         torch.cuda.synchronize()
         fri_const_ms = (time.perf_counter() - t0) / reps * 1e3
+        O.lib().so_set_threads(min(32, os.cpu_count() or 1))
         t0 = time.perf_counter()
         oroots, _, _ = O.fri_commit_np(cw.cpu().numpy().view(np.uint64), off0, omega0, 4, 64)
-        fri_cpu_ms = (time.perf_counter() - t0) * 1e3
+        fri_cpu_ms = (time.perf_counter() - t0) * 1e3  # (the reference arm probes the team size; this is the check)
         assert roots == oroots, "FRI commit roots differ from the oracle"
         # blake2b-only roof: register-resident chains of node compressions, 1024 threads per SM
         sms = torch.cuda.get_device_properties(dev).multi_processor_count

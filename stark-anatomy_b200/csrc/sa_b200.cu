@@ -1678,8 +1678,10 @@ static bool fri_tail_allowed(cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_tail_mu);
     if (g_tail_mode >= 0) return g_tail_mode == 1;
     g_tail_mode = 0;
-    if (const char *e = getenv("SA_FRI_PERSISTENT"))
-        if (atoi(e) == 0) return false;
+    // opt-in: measured on B200 (profiles/r02_notes.md, r02d) the persistent tail is no faster than one launch
+    // per round - the narrow rounds are blake2b dependency chains, not launch overhead
+    const char *e = getenv("SA_FRI_PERSISTENT");
+    if (!e || atoi(e) == 0) return false;
     uint64_t *page = nullptr, *page_dev = nullptr;
     if (cudaHostAlloc((void **)&page, 64, cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
