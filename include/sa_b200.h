@@ -72,6 +72,10 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
  * (a barrier across the ranks after the stream has drained).                                  */
 int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
                  const uint64_t root[2], int inverse, size_t batch, void *stream);
+/* Lets kernels of the CURRENT device store to memory of `peer_device` that is mapped into this process
+ * (cudaDeviceEnablePeerAccess; fine if it already is enabled).  A buffer opened from an IPC handle belongs to
+ * its owner's device ordinal in this process, and opening it does not enable access from another device.  */
+int sa_enable_peer_access(int peer_device);
 /* Same through HOST buffers: H2D copy, transforms, D2H copy, synchronises before
  * returning (the end-to-end call bench.py times as `e2e`).                               */
 int sa_ntt_host(void *out_host, const void *in_host, int log_n, const uint64_t root[2], int inverse,

@@ -1030,6 +1030,25 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     return ntt_run(out, in, log_n, root, inverse, batch, (cudaStream_t)stream, nullptr, 0);
 }
 
+int sa_enable_peer_access(int peer_device) {
+    int dev = 0;
+    SA_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return SA_OK;
+    int can = 0;
+    SA_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) {
+        g_last_error = "sa_enable_peer_access: no peer access between these devices";
+        return SA_ECUDA;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return SA_OK;
+    }
+    SA_CUDA(e);
+    return SA_OK;
+}
+
 int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
                  const uint64_t root[2], int inverse, size_t batch, void *stream) {
     if (nouts < 1 || nouts > TILE_MAX_PEERS + 1) return SA_ESIZE;

@@ -74,7 +74,13 @@ class PeerBuffers:
             dist.all_gather_object(handles, reduce_tensor(self.local[k]), group=group)
             row = []
             for q, (fn, args) in enumerate(handles):
-                row.append(self.local[k] if q == self.rank else fn(*args))
+                if q == self.rank:
+                    row.append(self.local[k])
+                    continue
+                peer = fn(*args)  # lives on rank q's device ordinal, mapped into this process
+                # kernels of THIS device will store into it (sa_ntt_multi): opening the handle does not enable that
+                eng._check(eng.lib.sa_enable_peer_access(peer.device.index))
+                row.append(peer)
             self.bufs.append(row)
         self.turn = 0
         self.flag = torch.zeros(1, dtype=torch.int32, device=eng.device)

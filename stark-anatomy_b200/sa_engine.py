@@ -37,6 +37,7 @@ SYMBOLS = [
     ("sa_launch_count", ctypes.c_uint64, []),
     ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_ntt_multi", _ci, [ctypes.POINTER(ctypes.c_void_p), _ci, _sz, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_enable_peer_access", _ci, [_ci]),
     ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_host_alloc", _vp, [_sz]),
     ("sa_host_free", _ci, [_vp]),

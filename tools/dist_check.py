@@ -43,7 +43,7 @@ try:
 except Exception as exc:
     peers = None
     report["peer_buffers_error"] = repr(exc)[:400]
-for mode in ("p2p-store", "p2p-copy", "nccl-pipelined", "nccl"):
+for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store"):  # (the plain ones first: a fault in a peer mode cannot hide them)
     if mode.startswith("p2p") and peers is None:
         continue
     try:
