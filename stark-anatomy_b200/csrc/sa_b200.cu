@@ -937,7 +937,17 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
     // measured on B200 (profiles/r01_notes.md, r01e_tile_shapes_tma_twiddles.jsonl): with the stage
     // twiddles in shared memory, 16-element register blocks on 4-column tiles (2 CTAs x 256 threads
     // per SM) win for the big tiles
-    if (LOGL >= 9) return launch_tile<LOGL, 4, 4>(a, st);
+    if constexpr (LOGL >= 9) {
+        // a job of less than ~two waves of four-column tiles: single-column CTAs balance the SMs better
+        // (SA_NTT_SMALL_TILES=0 turns this off; threshold in four-column tiles)
+        static const int small_max = [] {
+            const char *e = getenv("SA_NTT_SMALL_TILES");
+            return e ? atoi(e) : 0;
+        }();
+        const long long tiles4 = (long long)((a.ncols + 3) / 4) * a.nbatch;
+        if (small_max > 0 && tiles4 <= small_max) return launch_tile<LOGL, 4, 1>(a, st);
+        return launch_tile<LOGL, 4, 4>(a, st);
+    }
     return launch_tile<LOGL, 4, 8>(a, st);
 }
 static int launch_tile_dyn(int logl, const TileArgs &a, cudaStream_t st) {

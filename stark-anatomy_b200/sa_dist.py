@@ -174,12 +174,17 @@ def _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, l
             main.wait_stream(side[q])
 
 
+_COMM_STREAMS = {}
+
+
 def _ntt_nccl_pipelined(eng, vectors, log_n, root, inverse, n, per, rank, world, group):
     import torch
     dist = _dist()
     out = eng.empty(per * world * n)
     main = torch.cuda.current_stream()
-    comm = torch.cuda.Stream()
+    comm = _COMM_STREAMS.get(main.device)
+    if comm is None:
+        comm = _COMM_STREAMS[main.device] = torch.cuda.Stream()
     works = []
     for i in range(per):
         b = i * world + rank  # cyclic ownership: chunk i of every rank is contiguous in batch order
