@@ -6,10 +6,12 @@
 // emulation of the kernels' phase functions).
 //
 // Multiplication is Montgomery (R = 2^128) specialised to this prime:
-//   p = 1 + P3 * 2^96 with P3 = 407 << 23 = 0xCB800000, so
-//   -p^-1 mod 2^128 = P3 * 2^96 - 1, the Montgomery quotient is
-//   m = ((t0 * P3 mod 2^32) << 96) - t_lo, and m * p = m + (m * P3) << 96:
-//   the whole reduction costs four 32x32 multiplies by the constant P3.
+//   p = 1 + P3 * 2^96 with P3 = 407 << 23 = 0xCB800000, so p^-1 mod 2^128 = 1 - P3 * 2^96.
+//   The device code reduces with +p^-1: m = t_lo * p^-1 mod 2^128 is t_lo with (t0 * P3 mod 2^32) taken
+//   off its top word, and t * 2^-128 = t_hi - ((m * P3) >> 32) - borrow, in (-p, p): four multiplies by
+//   the constant P3 and one masked add of p (fe_montmul below).  The portable version (host, tests/emu,
+//   sa_selftest_field) uses the textbook -p^-1 form, m = ((t0 * P3 mod 2^32) << 96) - t_lo; both return the
+//   canonical residue of a * b * 2^-128.
 // Twiddles are stored pre-multiplied by R ("Montgomery form"), data stays in
 // canonical form: montmul(x, w*R) = x*w, so no conversion passes are needed and
 // every result is the canonical residue the reference's Python ints produce.

@@ -8,6 +8,13 @@ reference; every transform, Hadamard product, coset scaling and element-wise
 division runs in the sm_100a kernels behind include/sa_b200.h.  No CPU fallback:
 without the CUDA library the first call raises.
 
+Known divergence, in misuse only: when ``root_order`` is too small for the operands (degree >= root_order)
+the reference's NTT product wraps around silently (ntt.py:47-64 has no check) or trips an assert deep inside a
+recursive call, depending on the sizes; ``fast_zerofier`` / ``fast_evaluate`` / ``fast_interpolate`` here do not go
+through ``fast_multiply`` and return the mathematically correct polynomial / values in those cases (the two
+asserts on ``primitive_root`` / ``root_order`` themselves are the reference's).  ``fast_multiply`` and
+``fast_coset_divide`` wrap exactly like the reference.
+
 Reference lines mirrored: ntt :3-18, intt :20-30, fast_multiply :32-64,
 fast_zerofier :66-80, fast_evaluate :82-100, fast_interpolate :102-130,
 fast_coset_evaluate :132-135, fast_coset_divide :137-176.
