@@ -72,9 +72,20 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
  * (a barrier across the ranks after the stream has drained).                                  */
 int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
                  const uint64_t root[2], int inverse, size_t batch, void *stream);
+/* Buffers shared between the processes of one box (one process per GPU): sa_peer_alloc = cudaMalloc (zeroed) +
+ * CUDA IPC handle (64 bytes, to be sent to the other processes, e.g. with all_gather_object); sa_peer_open maps
+ * another process's buffer into the address space of the CURRENT device and enables peer access to its owner
+ * over NVLink, so that this device's kernels (sa_ntt_multi) and copy engines (sa_copy_async) can write it;
+ * sa_peer_close / sa_peer_free undo them.  sa_copy_async = cudaMemcpyAsync(cudaMemcpyDefault) on `stream`.   */
+int sa_peer_alloc(void **ptr, size_t bytes, uint8_t handle_out[64]);
+int sa_peer_open(void **ptr, const uint8_t handle[64]);
+int sa_peer_close(void *ptr);
+int sa_peer_free(void *ptr);
+int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 /* Lets kernels of the CURRENT device store to memory of `peer_device` that is mapped into this process
  * (cudaDeviceEnablePeerAccess; fine if it already is enabled).  A buffer opened from an IPC handle belongs to
- * its owner's device ordinal in this process, and opening it does not enable access from another device.  */
+ * its owner's device ordinal in this process, and opening it under that ordinal does not enable access from
+ * another device (sa_peer_open opens under the accessing device instead, which does).                        */
 int sa_enable_peer_access(int peer_device);
 /* Same through HOST buffers: H2D copy, transforms, D2H copy, synchronises before
  * returning (the end-to-end call bench.py times as `e2e`).                               */

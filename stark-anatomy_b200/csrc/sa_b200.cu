@@ -1040,6 +1040,44 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
     return ntt_run(out, in, log_n, root, inverse, batch, (cudaStream_t)stream, nullptr, 0);
 }
 
+// ---- buffers shared between the processes of one box (one process per GPU) ----
+int sa_peer_alloc(void **ptr, size_t bytes, uint8_t handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    *ptr = nullptr;
+    SA_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));  // (IPC needs a cudaMalloc allocation of its own, not a pool block)
+    SA_CUDA(cudaMemset(*ptr, 0, bytes ? bytes : 1));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        SA_CUDA(e);
+    }
+    memcpy(handle_out, &h, 64);
+    return SA_OK;
+}
+int sa_peer_open(void **ptr, const uint8_t handle[64]) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *ptr = nullptr;
+    // opened with THIS device current: the mapping lands in this device's address space and peer access to
+    // the owner is enabled on the way, which is what lets this device's kernels store into it
+    SA_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SA_OK;
+}
+int sa_peer_close(void *ptr) {
+    if (ptr) SA_CUDA(cudaIpcCloseMemHandle(ptr));
+    return SA_OK;
+}
+int sa_peer_free(void *ptr) {
+    if (ptr) SA_CUDA(cudaFree(ptr));
+    return SA_OK;
+}
+int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes) SA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return SA_OK;
+}
+
 int sa_enable_peer_access(int peer_device) {
     int dev = 0;
     SA_CUDA(cudaGetDevice(&dev));

@@ -6,8 +6,8 @@ GPU, ``torch.distributed``) runs its slice of the batch with no communication du
 What is left is ASSEMBLY: the caller wants the transformed batch on every rank.  Four ways to do
 it, all bit-exact (``assemble=`` of ``sharded_ntt``):
 
-  "p2p-store"  the product.  Every rank maps the other ranks' output buffers (CUDA IPC over NVLink /
-               NVSwitch, ``PeerBuffers``) and the LAST pass of its transforms stores each result tile
+  "p2p-store"  the product.  Every rank maps the other ranks' output buffers into its own device's address
+               space (CUDA IPC over NVLink / NVSwitch, ``PeerBuffers``) and the LAST pass of its transforms stores each result tile
                to all of them (``sa_ntt_multi``): compute and assembly are one kernel, the NVLink
                writes overlap the butterflies tile by tile, no gather pass exists.
   "p2p-copy"   transforms go to the local buffer; as soon as transform i is done the copy engines push it
@@ -48,40 +48,47 @@ def _rank_world(group=None):
 class PeerBuffers:
     """``count`` symmetric device buffers of ``nelems`` field elements, each mapped on every rank.
 
-    Rank r allocates its buffers with torch, exports them as CUDA IPC handles
-    (``torch.multiprocessing.reductions.reduce_tensor``), the handles travel through
-    ``all_gather_object`` and every other rank opens them (peer access over NVLink is enabled by
-    the open).  ``bufs[k][q]`` is rank q's k-th buffer as a tensor usable from THIS process.
-    Two buffers alternate between calls so that a rank may still read call k's result while
-    another rank already writes call k+1 (see ``sharded_ntt``).
+    Rank r allocates its buffers through the C library (``sa_peer_alloc``: ``cudaMalloc`` + CUDA IPC handle),
+    the 64-byte handles travel through ``all_gather_object`` and every other rank opens them with ITS device
+    current (``sa_peer_open``: ``cudaIpcOpenMemHandle`` with lazy peer access), which maps the memory into that
+    device's address space over NVLink / NVSwitch so that its kernels and copy engines can write it.
+    ``local[k]`` is this rank's k-th buffer as a tensor, ``ptrs[k][q]`` rank q's k-th buffer as a raw device
+    pointer valid in THIS process.  Two buffers alternate between calls so that a rank may still read call k's
+    result while another rank already writes call k+1 (see ``sharded_ntt``).
     """
 
     def __init__(self, nelems, group=None, count=2):
+        import ctypes
         import torch
-        from torch.multiprocessing.reductions import reduce_tensor
         dist = _dist()
         eng = sa_engine.get_engine()
+        lib = eng.lib
         self.group = group
         self.rank, self.world = _rank_world(group)
         self.nelems = nelems
-        self.local = [torch.zeros((nelems, 2), dtype=torch.int64, device=eng.device) for _ in range(count)]
-        self.bufs = []
+        self.eng = eng
+        self._own, self._opened = [], []
+        self.local, self.ptrs = [], []
+        eng._stream()  # (pins the current device)
         for k in range(count):
-            if self.world == 1:
-                self.bufs.append([self.local[k]])
-                continue
-            handles = [None] * self.world
-            dist.all_gather_object(handles, reduce_tensor(self.local[k]), group=group)
-            row = []
-            for q, (fn, args) in enumerate(handles):
-                if q == self.rank:
-                    row.append(self.local[k])
-                    continue
-                peer = fn(*args)  # lives on rank q's device ordinal, mapped into this process
-                # kernels of THIS device will store into it (sa_ntt_multi): opening the handle does not enable that
-                eng._check(eng.lib.sa_enable_peer_access(peer.device.index))
-                row.append(peer)
-            self.bufs.append(row)
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            eng._check(lib.sa_peer_alloc(ctypes.byref(ptr), 16 * nelems, handle))
+            self._own.append(ptr.value)
+            self.local.append(eng.wrap_pointer(ptr.value, nelems))
+            row = [None] * self.world
+            row[self.rank] = ptr.value
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                for q, h in enumerate(handles):
+                    if q == self.rank:
+                        continue
+                    peer = ctypes.c_void_p()
+                    eng._check(lib.sa_peer_open(ctypes.byref(peer), h))
+                    self._opened.append(peer.value)
+                    row[q] = peer.value
+            self.ptrs.append(row)
         self.turn = 0
         self.flag = torch.zeros(1, dtype=torch.int32, device=eng.device)
         self.side = None
@@ -90,10 +97,10 @@ class PeerBuffers:
             dist.barrier(group=group)  # every rank has opened every handle before anybody writes
 
     def next(self):
-        """(local buffer, [rank q's buffer for q in range(world)]) of this call"""
+        """(local buffer as a tensor, [rank q's buffer as a device pointer for q in range(world)]) of this call"""
         k = self.turn
         self.turn = (self.turn + 1) % len(self.local)
-        return self.local[k], self.bufs[k]
+        return self.local[k], self.ptrs[k]
 
     def fence(self):
         """stream-ordered barrier across the ranks (a 4-byte NCCL all-reduce on the current stream): when it
@@ -105,8 +112,24 @@ class PeerBuffers:
         import torch
         if self.side is None:
             self.side = [torch.cuda.Stream() for _ in range(self.world)]
-            self.events = [torch.cuda.Event() for _ in range(self.world + 1)]
         return self.side
+
+    def close(self):
+        """unmap the peers' buffers and free the own ones (every rank, after a barrier: nobody may still write)"""
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            _dist().barrier(group=self.group)
+        lib = self.eng.lib
+        for p in self._opened:
+            lib.sa_peer_close(p)
+        self._opened = []
+        if self.world > 1:
+            _dist().barrier(group=self.group)
+        self.local = []
+        for p in self._own:
+            lib.sa_peer_free(p)
+        self._own = []
 
 
 # ------------------------------------------------------------------------------- sharded transforms
@@ -144,7 +167,7 @@ def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None, as
     mine = eng.slice(vectors, lo * n, (lo + per) * n)
     local, bufs = peers.next()
     if assemble == "p2p-store":
-        outs = [local] + [bufs[q] for q in range(world) if q != rank]
+        outs = [bufs[rank]] + [bufs[q] for q in range(world) if q != rank]
         eng.ntt_multi(outs, lo * n, mine, log_n, root, inverse=inverse, batch=per)
     elif assemble == "p2p-copy":
         _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world)
@@ -155,6 +178,7 @@ def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None, as
 
 
 def _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world):
+    import ctypes
     import torch
     side = peers.streams()
     main = torch.cuda.current_stream()
@@ -163,12 +187,13 @@ def _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, l
         eng.ntt_into(dst, mine[i * n:(i + 1) * n], log_n, root, inverse=inverse)
         ev = torch.cuda.Event()
         ev.record(main)
+        off = 16 * (lo + i) * n
         for q in range(world):
             if q == rank:
                 continue
-            with torch.cuda.stream(side[q]):
-                side[q].wait_event(ev)
-                bufs[q][(lo + i) * n:(lo + i + 1) * n].copy_(dst, non_blocking=True)
+            side[q].wait_event(ev)  # the copy engine pushes transform i to rank q under transform i + 1
+            eng._check(eng.lib.sa_copy_async(bufs[q] + off, bufs[rank] + off, 16 * n,
+                                             ctypes.c_void_p(side[q].cuda_stream)))
     for q in range(world):
         if q != rank:
             main.wait_stream(side[q])

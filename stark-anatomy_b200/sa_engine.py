@@ -38,6 +38,11 @@ SYMBOLS = [
     ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_ntt_multi", _ci, [ctypes.POINTER(ctypes.c_void_p), _ci, _sz, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_enable_peer_access", _ci, [_ci]),
+    ("sa_peer_alloc", _ci, [ctypes.POINTER(ctypes.c_void_p), _sz, ctypes.c_char_p]),
+    ("sa_peer_open", _ci, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    ("sa_peer_close", _ci, [_vp]),
+    ("sa_peer_free", _ci, [_vp]),
+    ("sa_copy_async", _ci, [_vp, _vp, _sz, _vp]),
     ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_host_alloc", _vp, [_sz]),
     ("sa_host_free", _ci, [_vp]),
@@ -107,7 +112,12 @@ class CudaEngine:
 
     # ------------------------------------------------------------ plumbing
     def _stream(self):
-        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        # the C library works on the CURRENT device; make sure that is this engine's (a peer tensor rebuilt from
+        # an IPC handle, or user code, may have left another device current)
+        cuda = self.torch.cuda
+        if cuda.current_device() != self.device.index:
+            cuda.set_device(self.device)
+        return ctypes.c_void_p(cuda.current_stream(self.device).cuda_stream)
 
     def _check(self, rc):
         if rc == 0:
@@ -175,12 +185,18 @@ class CudaEngine:
         return out
 
     def ntt_multi(self, outs, out_offset, vec, log_n, root, inverse=False, batch=1):
-        """sa_ntt_multi: transform `vec` and store the result at element offset `out_offset` of every tensor in
-        `outs` (outs[0] on this device, the others peer-mapped buffers of other GPUs)"""
+        """sa_ntt_multi: transform `vec` and store the result at element offset `out_offset` of every buffer in
+        `outs` (outs[0] on this device, the others peer-mapped buffers of other GPUs; tensors or raw pointers)"""
         vec = vec.contiguous()
-        ptrs = (ctypes.c_void_p * len(outs))(*[int(t.data_ptr()) for t in outs])
+        ptrs = (ctypes.c_void_p * len(outs))(*[int(t) if isinstance(t, int) else int(t.data_ptr()) for t in outs])
         self._check(self.lib.sa_ntt_multi(ptrs, len(outs), out_offset, vec.data_ptr(), log_n, _limbs(root),
                                           int(bool(inverse)), batch, self._stream()))
+
+    def wrap_pointer(self, ptr, nelems):
+        """a device vector (torch.int64[n, 2]) over memory this process got from the C library"""
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (nelems, 2), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+        return self.torch.as_tensor(_Raw(), device=self.device)
 
     def pointwise_mul(self, a, b):
         out = self.empty(a.shape[0])

@@ -12,7 +12,8 @@ rank, world = dist.get_rank(), dist.get_world_size()
 stage = sys.argv[1] if len(sys.argv) > 1 else "all"
 def say(msg):
     print("[rank %d] %s" % (rank, msg), flush=True)
-log_n, batch = 16, 4 * world
+log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+batch = 4 * world if log_n < 20 else 16
 n = 1 << log_n
 rng = np.random.default_rng(3)
 x = np.stack([rng.integers(0, 1 << 64, size=batch * n, dtype=np.uint64), rng.integers(0, 0xCB80000000000000, size=batch * n, dtype=np.uint64)], axis=1)
@@ -28,9 +29,10 @@ if stage in ("all", "nccl"):
     say("nccl mode"); check("nccl", sa_dist.sharded_ntt(vx, log_n, w, assemble="nccl"))
     say("nccl-pipelined mode"); check("nccl-pipelined", sa_dist.sharded_ntt(vx, log_n, w, assemble="nccl-pipelined"))
 if stage in ("all", "peers"):
-    say("PeerBuffers"); peers = sa_dist.PeerBuffers(batch * n); torch.cuda.synchronize(); say("PeerBuffers ok: devices %s" % [str(t.device) for t in peers.bufs[0]])
-    say("torch copy into a peer buffer"); q = (rank + 1) % world
-    peers.bufs[0][q][rank * 8:rank * 8 + 8].copy_(vx[:8]); torch.cuda.synchronize(); dist.barrier(); say("peer copy ok")
+    say("PeerBuffers"); peers = sa_dist.PeerBuffers(batch * n); torch.cuda.synchronize(); say("PeerBuffers ok")
+    say("copy engine into a peer buffer"); q = (rank + 1) % world
+    import ctypes
+    eng._check(eng.lib.sa_copy_async(peers.ptrs[0][q] + 128 * rank, vx.data_ptr(), 128, None)); torch.cuda.synchronize(); dist.barrier(); say("peer copy ok")
     say("nccl after PeerBuffers"); check("nccl", sa_dist.sharded_ntt(vx, log_n, w, assemble="nccl"))
     say("p2p-copy"); check("p2p-copy", sa_dist.sharded_ntt(vx, log_n, w, assemble="p2p-copy", peers=peers))
     say("p2p-store"); check("p2p-store", sa_dist.sharded_ntt(vx, log_n, w, assemble="p2p-store", peers=peers))
