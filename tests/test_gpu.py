@@ -210,6 +210,30 @@ def test_ntt_multi_stores_every_destination(eng, log_n, batch, nouts):
         eng.ntt_multi(outs * 9, 0, up(eng, x), log_n, w, batch=batch)
 
 
+def test_peer_buffers_single_process(eng):
+    """the library-side pieces of sa_dist.PeerBuffers that one process can exercise: sa_peer_alloc (zeroed cudaMalloc
+    + IPC handle), a torch view over it, sa_copy_async, sa_ntt_multi into it, free.  (Opening the handles from the
+    other ranks needs several processes: tools/dist_check.py under torchrun.)"""
+    import sa_dist
+    n, batch = 1 << 12, 4
+    pb = sa_dist.PeerBuffers(n * batch)
+    assert pb.world == 1 and len(pb.local) == 2 and pb.ptrs[0][0] == pb.local[0].data_ptr()
+    assert int(pb.local[0].abs().sum().item()) == 0
+    x = rand_np(5150, n * batch)
+    w = O.primitive_nth_root(n)
+    local, ptrs = pb.next()
+    eng.ntt_multi([ptrs[0]], 0, up(eng, x), 12, w, batch=batch)
+    want = O.ntt_batch_np(w, x.reshape(batch, n, 2)).reshape(-1, 2)
+    assert (down(eng, local) == want).all()
+    local2, ptrs2 = pb.next()
+    assert ptrs2[0] != ptrs[0]
+    eng._check(eng.lib.sa_copy_async(ptrs2[0], ptrs[0], 16 * n * batch, eng._stream()))
+    assert (down(eng, local2) == want).all()
+    full = sa_dist.sharded_ntt(up(eng, x), 12, w, assemble="p2p-store", peers=pb)  # world 1: plain transform
+    assert (down(eng, full) == want).all()
+    pb.close()
+
+
 @pytest.mark.parametrize("log_n,batch", [(16, 70), (18, 9), (12, 3), (21, 3), (22, 2)])
 def test_ntt_host_entry_chunk_pipeline(eng, log_n, batch):
     """sa_ntt_host cuts a batch into ramped chunks over several copy streams (32 MiB chunks, first and
