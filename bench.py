@@ -244,6 +244,11 @@ def allgather_leg(eng, dist, rank, world, w, reps=20):
         except Exception as exc:
             res["modes"][mode] = {"error": repr(exc)[:300]}
             torch.cuda.synchronize()
+    if peers is not None:
+        try:
+            peers.close()
+        except Exception:
+            pass
     ok = {m: v["ms_per_call"] for m, v in res["modes"].items() if "ms_per_call" in v}
     if ok:
         best = min(ok, key=ok.get)

@@ -944,6 +944,12 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
             const char *e = getenv("SA_NTT_SMALL_TILES");
             return e ? atoi(e) : 0;
         }();
+        // multi-GPU assembly (sa_ntt_multi): SA_NTT_PEER_C=8 stores 128-byte instead of 64-byte segments to the peers
+        static const int peer_c = [] {
+            const char *e = getenv("SA_NTT_PEER_C");
+            return e ? atoi(e) : 4;
+        }();
+        if (a.npeer > 0 && peer_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
         const long long tiles4 = (long long)((a.ncols + 3) / 4) * a.nbatch;
         if (small_max > 0 && tiles4 <= small_max) return launch_tile<LOGL, 4, 1>(a, st);
         return launch_tile<LOGL, 4, 4>(a, st);
