@@ -446,7 +446,12 @@ __device__ __forceinline__ void merkle_chunk_body(const MerkleArgs &a, const lon
     if (a.root_out && tid == 0) merkle_publish_root(a, sm);
 }
 
-__global__ void __launch_bounds__(MK_THREADS) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
+// SA_MK_MINB: minimum resident CTAs per SM the register allocator has to leave room for (experiments:
+// 3 -> <= 85 registers, 24 warps per SM instead of 16)
+#ifndef SA_MK_MINB
+#define SA_MK_MINB 1
+#endif
+__global__ void __launch_bounds__(MK_THREADS, SA_MK_MINB) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
     __shared__ uint64_t sm[MK_THREADS * 8];
     merkle_chunk_body(a, blockIdx.x, gridDim.x, sm);
 }
