@@ -97,18 +97,23 @@ void blake2b_single_block(uint64_t out[8], const uint64_t m[16], uint32_t len) {
 // zeros ("0" for zero), packed little-endian into w[0..4] (40 bytes, zero padded).
 // Returns the length in bytes (1..39).   code/algebra.py:53-57
 SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
-    // base-1e9 limbs, least significant first; 2^128 < 1e39 so five limbs (9,9,9,9,3 digits)
+    // base-1e9 limbs, least significant first; 2^128 < 1e39 so five limbs (9,9,9,9,3 digits).
+    // After k limbs have been taken off, the quotient is below 2^128 / 1e9^k = 2^98.1, 2^68.2, 2^38.3, 2^8.4:
+    // its top words are known to be zero, so the long divisions run over 4, 4, 3 and 2 words and the last limb
+    // is the remaining quotient itself (13 divisions by a constant instead of 20).
     uint32_t q[4] = {x.v[0], x.v[1], x.v[2], x.v[3]};
     uint32_t chunk[5];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 4; k++) {
+        const int top = k <= 1 ? 3 : (k == 2 ? 2 : 1);
         uint64_t rem = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int i = 3; i >= 0; i--) {
+            if (i > top) continue;
             const uint64_t cur = (rem << 32) | q[i];
             const uint64_t d = cur / 1000000000ULL;
             q[i] = (uint32_t)d;
@@ -116,6 +121,7 @@ SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
         }
         chunk[k] = (uint32_t)rem;
     }
+    chunk[4] = q[0];  // < 341
     // 48 character slots, right aligned: slots 3..47 hold the 45 zero-padded digits
     // (slot index = byte index in the 6-word buffer below)
     uint64_t buf[6] = {0, 0, 0, 0, 0, 0};
@@ -129,6 +135,7 @@ SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
 #pragma unroll
 #endif
         for (int j = 0; j < 9; j++) {
+            if (k == 4 && j >= 3) continue;  // the top limb has three digits
             const uint32_t nq = cval / 10u;
             const uint32_t dig = cval - nq * 10u;
             cval = nq;
