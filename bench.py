@@ -214,7 +214,7 @@ def allgather_leg(eng, dist, rank, world, w, reps=20):
     check = sorted({BATCH - 1, BATCH // 2, 0})
     want = {b: O.ntt_np(w, xg[b * N:(b + 1) * N].cpu().numpy().view(np.uint64), parallel=True) for b in check} if rank == 0 else {}
     stream = torch.cuda.current_stream()
-    for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store"):  # (the plain ones first: a fault in a peer mode cannot hide them)
+    for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store", "p2p-push"):  # (the plain ones first: a fault in a peer mode cannot hide them)
         if mode.startswith("p2p") and peers is None:
             continue
         try:

@@ -82,6 +82,11 @@ int sa_peer_open(void **ptr, const uint8_t handle[64]);
 int sa_peer_close(void *ptr);
 int sa_peer_free(void *ptr);
 int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+/* One kernel that reads `bytes` (multiple of 16, 16-byte aligned) at src once and stores them to every dsts[i],
+ * i < ndst <= 7 (peer-mapped buffers): fully coalesced stores, a warp writes 512 contiguous bytes per
+ * destination.  The push half of sa_dist's "p2p-push" assembly: transform i is pushed on a side stream while
+ * transform i + 1 computes.  SA_PUSH_CTAS = CTAs of the push kernel (default 148).                          */
+int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *stream);
 /* Lets kernels of the CURRENT device store to memory of `peer_device` that is mapped into this process
  * (cudaDeviceEnablePeerAccess; fine if it already is enabled).  A buffer opened from an IPC handle belongs to
  * its owner's device ordinal in this process, and opening it under that ordinal does not enable access from

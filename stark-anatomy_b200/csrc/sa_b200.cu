@@ -268,6 +268,34 @@ __global__ void __launch_bounds__(256) k_interp_colsum(fe *out, const fe *QT, in
     }
     if (tid == 0) tile_st(out + m, red[0]);
 }
+// ---- multi-GPU assembly by push: one read of a finished block, one fully coalesced 16-byte store per lane
+// and destination (a warp writes 512 contiguous bytes to every peer: NVLink sees whole packets, unlike the 64-byte
+// segments the transform's own last pass produces)
+struct PushArgs {
+    uint4 *dst[TILE_MAX_PEERS];
+    int ndst;
+};
+__global__ void __launch_bounds__(256) k_push(const __grid_constant__ PushArgs a, const uint4 *src, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {  // four loads in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldcs(src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int p = 0; p < TILE_MAX_PEERS; p++)
+                if (p < a.ndst) a.dst[p][i + u * stride] = v[u];
+    }
+    for (; i < n16; i += stride) {
+        const uint4 v = __ldcs(src + i);
+#pragma unroll
+        for (int p = 0; p < TILE_MAX_PEERS; p++)
+            if (p < a.ndst) a.dst[p][i] = v;
+    }
+}
+
 // ---- subproduct tree over a domain of k points (fast_zerofier / fast_interpolate, ntt.py:66-130) ----
 // The k points sit in the first k of K = 2^ceil(log2 k) leaf slots.  Level j has K >> j nodes of
 // m = 2^j coefficients each, stored back to back.  A node whose leaf range lies completely inside the
@@ -1086,6 +1114,28 @@ int sa_peer_free(void *ptr) {
 }
 int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes) SA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return SA_OK;
+}
+
+int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *stream) {
+    if (ndst < 0 || ndst > TILE_MAX_PEERS || (bytes & 15) || (((uintptr_t)src) & 15)) return SA_ESIZE;
+    if (ndst == 0 || bytes == 0) return SA_OK;
+    PushArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ndst = ndst;
+    for (int i = 0; i < ndst; i++) {
+        if (((uintptr_t)dsts[i]) & 15) return SA_ESIZE;
+        a.dst[i] = (uint4 *)dsts[i];
+    }
+    static const int ctas = [] {
+        const char *e = getenv("SA_PUSH_CTAS");
+        return e && atoi(e) > 0 ? atoi(e) : 148;
+    }();
+    const size_t n16 = bytes / 16;
+    size_t grid = (n16 + 255) / 256;
+    if (grid > (size_t)ctas) grid = (size_t)ctas;
+    k_push<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, (const uint4 *)src, n16);
+    SA_LAUNCH_CHECK();
     return SA_OK;
 }
 

@@ -10,8 +10,10 @@ it, all bit-exact (``assemble=`` of ``sharded_ntt``):
                space (CUDA IPC over NVLink / NVSwitch, ``PeerBuffers``) and the LAST pass of its transforms stores each result tile
                to all of them (``sa_ntt_multi``): compute and assembly are one kernel, the NVLink
                writes overlap the butterflies tile by tile, no gather pass exists.
-  "p2p-copy"   transforms go to the local buffer; as soon as transform i is done the copy engines push it
-               to every peer (one stream per peer) while transform i+1 computes.
+  "p2p-push"   transforms go to the local buffer; as soon as transform i is done ONE push kernel (``sa_push``:
+               one read, a fully coalesced store per peer) sends it to all peers on a high-priority side
+               stream while transform i+1 computes.
+  "p2p-copy"   the same with the copy engines (one ``cudaMemcpyAsync`` and stream per peer).
   "nccl-pipelined"  cyclic ownership (rank r owns transforms r, r + world, ...), so chunk i of every rank
                is one in-place ``all_gather_into_tensor`` that runs on a side stream under chunk i+1.
   "nccl"       round 1's baseline: transform the contiguous slice, then ONE all-gather (also the only mode for
@@ -114,6 +116,13 @@ class PeerBuffers:
             self.side = [torch.cuda.Stream() for _ in range(self.world)]
         return self.side
 
+    def push_stream(self):
+        """high-priority side stream of the push kernels (their CTAs take the SM slots the compute kernel frees)"""
+        import torch
+        if getattr(self, "_push", None) is None:
+            self._push = torch.cuda.Stream(priority=-1)
+        return self._push
+
     def close(self):
         """unmap the peers' buffers and free the own ones (every rank, after a barrier: nobody may still write)"""
         import torch
@@ -171,6 +180,8 @@ def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None, as
         eng.ntt_multi(outs, lo * n, mine, log_n, root, inverse=inverse, batch=per)
     elif assemble == "p2p-copy":
         _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world)
+    elif assemble == "p2p-push":
+        _ntt_p2p_push(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world)
     else:
         raise ValueError("unknown assemble mode %r" % assemble)
     peers.fence()
@@ -197,6 +208,24 @@ def _ntt_p2p_copy(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, l
     for q in range(world):
         if q != rank:
             main.wait_stream(side[q])
+
+
+def _ntt_p2p_push(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo, rank, world):
+    import ctypes
+    import torch
+    side = peers.push_stream()
+    main = torch.cuda.current_stream()
+    others = [q for q in range(world) if q != rank]
+    for i in range(per):
+        dst = local[(lo + i) * n:(lo + i + 1) * n]
+        eng.ntt_into(dst, mine[i * n:(i + 1) * n], log_n, root, inverse=inverse)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        off = 16 * (lo + i) * n
+        dsts = (ctypes.c_void_p * len(others))(*[bufs[q] + off for q in others])
+        eng._check(eng.lib.sa_push(dsts, len(others), bufs[rank] + off, 16 * n, ctypes.c_void_p(side.cuda_stream)))
+    main.wait_stream(side)
 
 
 _COMM_STREAMS = {}

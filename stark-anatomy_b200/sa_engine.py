@@ -43,6 +43,7 @@ SYMBOLS = [
     ("sa_peer_close", _ci, [_vp]),
     ("sa_peer_free", _ci, [_vp]),
     ("sa_copy_async", _ci, [_vp, _vp, _sz, _vp]),
+    ("sa_push", _ci, [ctypes.POINTER(ctypes.c_void_p), _ci, _vp, _sz, _vp]),
     ("sa_ntt_host", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_host_alloc", _vp, [_sz]),
     ("sa_host_free", _ci, [_vp]),

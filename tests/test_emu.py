@@ -105,7 +105,7 @@ def test_decimal_and_leaf(E):
     rng = random.Random(6)
     vals = [0, 1, 9, 10, 99, 100, 10**9 - 1, 10**9, 10**18, 10**19 - 1, 10**19, 10**27, 10**36, 10**38 - 1,
             10**38, P - 1, P - 2, 2**32 - 1, 2**32, 2**64 - 1, 2**64, 2**96 - 1, 2**96, 2**127, 10**9 * (2**32 - 1),
-            (10**9 - 1) * 10**27 + 5, 340 * 10**36 + 10**36 - 1] + [rng.randrange(P) for _ in range(500)] + \
+            (10**9 - 1) * 10**27 + 5, 2**128 - 1, 340 * 10**36] + [rng.randrange(P) for _ in range(500)] + \
            [rng.randrange(10**k) for k in range(1, 39) for _ in range(10)]
     for v in vals:
         buf = np.zeros(40, dtype=np.uint8)

@@ -229,6 +229,19 @@ def test_peer_buffers_single_process(eng):
     assert ptrs2[0] != ptrs[0]
     eng._check(eng.lib.sa_copy_async(ptrs2[0], ptrs[0], 16 * n * batch, eng._stream()))
     assert (down(eng, local2) == want).all()
+    # sa_push: one read, several destinations (here three windows of the second buffer), ragged tail
+    import ctypes
+    import torch
+    local2.zero_()
+    nbytes = 16 * (n + 5)
+    dsts = (ctypes.c_void_p * 3)(ptrs2[0], ptrs2[0] + 16 * (n + 8), ptrs2[0] + 16 * (2 * n + 16))
+    eng._check(eng.lib.sa_push(dsts, 3, ptrs[0], nbytes, eng._stream()))
+    got = down(eng, local2)
+    for k in range(3):
+        o = k * (n + 8)
+        assert (got[o:o + n + 5] == want[:n + 5]).all() and (got[o + n + 5:o + n + 8] == 0).all()
+    with pytest.raises(AssertionError, match="unsupported size"):
+        eng._check(eng.lib.sa_push(dsts, 3, ptrs[0], 24, eng._stream()))
     full = sa_dist.sharded_ntt(up(eng, x), 12, w, assemble="p2p-store", peers=pb)  # world 1: plain transform
     assert (down(eng, full) == want).all()
     pb.close()

@@ -43,7 +43,8 @@ try:
 except Exception as exc:
     peers = None
     report["peer_buffers_error"] = repr(exc)[:400]
-for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store"):  # (the plain ones first: a fault in a peer mode cannot hide them)
+MODES = os.environ.get("SA_DIST_MODES", "nccl,nccl-pipelined,p2p-copy,p2p-store,p2p-push").split(",")
+for mode in MODES:  # (the plain ones first: a fault in a peer mode cannot hide them)
     if mode.startswith("p2p") and peers is None:
         continue
     try:
@@ -75,7 +76,10 @@ for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store"):  # (the plain o
         torch.cuda.synchronize()
 
 # independent FRI instances, one transcript each (2^16 codewords, 4 per rank)
+report["env"] = {k: v for k, v in os.environ.items() if k.startswith(("SA_NTT_PEER", "SA_PUSH"))}
 try:
+    if os.environ.get("SA_DIST_SKIP_FRI") == "1":
+        raise RuntimeError("skipped")
     import hashlib
     import pickle
     import sa_host
