@@ -977,10 +977,12 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
             const char *e = getenv("SA_NTT_SMALL_TILES");
             return e ? atoi(e) : 0;
         }();
-        // multi-GPU assembly (sa_ntt_multi): SA_NTT_PEER_C=8 stores 128-byte instead of 64-byte segments to the peers
+        // multi-GPU assembly (sa_ntt_multi): 8-column tiles store 128-byte instead of 64-byte segments to the
+        // peers - the pass is bound by NVLink, not by the butterflies (8 GPUs, 16 x 2^20 incl. assembly: 0.468 ms
+        // against 0.665 ms with 4-column tiles, profiles/r02_notes.md); SA_NTT_PEER_C=4 for the comparison
         static const int peer_c = [] {
             const char *e = getenv("SA_NTT_PEER_C");
-            return e ? atoi(e) : 4;
+            return e ? atoi(e) : 8;
         }();
         if (a.npeer > 0 && peer_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
         const long long tiles4 = (long long)((a.ncols + 3) / 4) * a.nbatch;
