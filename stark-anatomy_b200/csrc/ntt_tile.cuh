@@ -70,11 +70,10 @@ struct TilePlan {
     static constexpr int NLOOP = NST - 1;          // full-radix stages that are not the last stage
     static constexpr int LASTLOG = REM ? REM : EL;  // log2 radix of the last stage
     static constexpr int TPT = (L / E) * C;        // threads per tile
-    // tiles per CTA: small tiles are packed into 128-thread CTAs - except single-column tiles of the big
-    // transforms (LOGL >= 9, C == 1), which exist for the opposite reason: a lone 2^20 transform is 256 four-column
-    // tiles per pass on 296 CTA slots (108 SMs carry two, 40 carry one); 1024 one-column CTAs of 64 threads spread
-    // as 7 / 6 per SM, 12.5 % less on the busiest SM
-    static constexpr int TPC = TPT >= 128 ? 1 : ((C == 1 && LOGL >= 9) ? 1 : 128 / TPT);
+    // tiles per CTA: small tiles are packed into 128-thread CTAs.  (Round 2 tried single-column CTAs of 64 threads
+    // for lone 2^20 transforms - 1024 CTAs spread 7 / 6 per SM instead of 256 four-column tiles 2 / 1 - and lost:
+    // 86 us against 60 us, the 16-byte-per-row accesses cost more than the balance gains.)
+    static constexpr int TPC = TPT >= 128 ? 1 : 128 / TPT;
     static constexpr int THREADS = TPT * TPC;
     // dynamic shared memory: the tile rows, then the stage-twiddle table (L elements, staged by one
     // bulk-async copy, see tile_stage_twiddles), then the 8-byte mbarrier it completes on

@@ -474,10 +474,11 @@ __device__ __forceinline__ void merkle_chunk_body(const MerkleArgs &a, const lon
     if (a.root_out && tid == 0) merkle_publish_root(a, sm);
 }
 
-// SA_MK_MINB: minimum resident CTAs per SM the register allocator has to leave room for (experiments:
-// 3 -> <= 85 registers, 24 warps per SM instead of 16)
+// SA_MK_MINB: minimum resident CTAs per SM the register allocator has to leave room for.  2 = at most 128
+// registers: without the bound the kernel drifted to 148 registers in round 2 (one CTA per SM, 2^20-leaf tree
+// 341 -> 383 us); 3 (<= 85 registers, 24 warps per SM) is an experiment
 #ifndef SA_MK_MINB
-#define SA_MK_MINB 1
+#define SA_MK_MINB 2
 #endif
 __global__ void __launch_bounds__(MK_THREADS, SA_MK_MINB) k_merkle_chunk(const __grid_constant__ MerkleArgs a) {
     __shared__ uint64_t sm[MK_THREADS * 8];
@@ -496,7 +497,7 @@ __device__ __forceinline__ bool fri_tail_spin(volatile const unsigned long long 
     }
     return true;
 }
-__global__ void __launch_bounds__(MK_THREADS) k_fri_tail(const __grid_constant__ FriTailArgs t) {
+__global__ void __launch_bounds__(MK_THREADS, 2) k_fri_tail(const __grid_constant__ FriTailArgs t) {
     __shared__ uint64_t sm[MK_THREADS * 8];
     __shared__ uint32_t s_sm[4];
     __shared__ int s_ok;
@@ -971,12 +972,6 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
     // twiddles in shared memory, 16-element register blocks on 4-column tiles (2 CTAs x 256 threads
     // per SM) win for the big tiles
     if constexpr (LOGL >= 9) {
-        // a job of less than ~two waves of four-column tiles: single-column CTAs balance the SMs better
-        // (SA_NTT_SMALL_TILES=0 turns this off; threshold in four-column tiles)
-        static const int small_max = [] {
-            const char *e = getenv("SA_NTT_SMALL_TILES");
-            return e ? atoi(e) : 0;
-        }();
         // multi-GPU assembly (sa_ntt_multi): 8-column tiles store 128-byte instead of 64-byte segments to the
         // peers - the pass is bound by NVLink, not by the butterflies (8 GPUs, 16 x 2^20 incl. assembly: 0.468 ms
         // against 0.665 ms with 4-column tiles, profiles/r02_notes.md); SA_NTT_PEER_C=4 for the comparison
@@ -985,8 +980,6 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
             return e ? atoi(e) : 8;
         }();
         if (a.npeer > 0 && peer_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
-        const long long tiles4 = (long long)((a.ncols + 3) / 4) * a.nbatch;
-        if (small_max > 0 && tiles4 <= small_max) return launch_tile<LOGL, 4, 1>(a, st);
         return launch_tile<LOGL, 4, 4>(a, st);
     }
     return launch_tile<LOGL, 4, 8>(a, st);
