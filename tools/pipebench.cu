@@ -28,13 +28,19 @@ enum {
     V_MIX_LO_IADD,    // one IMAD + one IADD3
     V_DFMA,           // fma.rn.f64
     V_MIX_WIDE_DFMA,  // one IMAD.WIDE + one DFMA
+    V_IND_WIDE_2LOP,  // one IMAD.WIDE (own chain) + two LOP3 on an INDEPENDENT chain: structural overlap of the pipes
+    V_IND_WIDE_4LOP,  // ... + four LOP3
+    V_IND_WIDEC_2LOP, // IMAD.WIDE with fused 64-bit addend (carry-chain form) + two independent LOP3
+    V_IND_LO_2LOP,    // one IMAD (lo) + two independent LOP3 (reference point)
     V_COUNT
 };
 static const char *NAMES[V_COUNT] = {"imad.wide rrr", "imad.wide imm", "imad.wide const", "imul.wide (no addend)",
                                       "imad.wide carry chain (lo.cc+madc.hi)", "imad lo", "imad hi", "iadd3",
                                       "iadd3.x carry chain", "lop3", "mix wide+iadd3", "mix wide+2 iadd3",
-                                      "mix imad.lo+iadd3", "dfma", "mix wide+dfma"};
-static const int INSTR_PER_SLOT[V_COUNT] = {1, 1, 1, 1, 1, 1, 1, 2, 4, 2, 2, 3, 2, 1, 2};
+                                      "mix imad.lo+iadd3", "dfma", "mix wide+dfma", "independent: wide + 2 lop3",
+                                      "independent: wide + 4 lop3", "independent: wide(carry form) + 2 lop3",
+                                      "independent: imad.lo + 2 lop3"};
+static const int INSTR_PER_SLOT[V_COUNT] = {1, 1, 1, 1, 1, 1, 1, 2, 4, 2, 2, 3, 2, 1, 2, 3, 5, 3, 3};
 
 template <int V>
 __global__ void __launch_bounds__(256) k_pipe(uint64_t *sink, uint32_t mult, int iters) {
@@ -92,6 +98,30 @@ __global__ void __launch_bounds__(256) k_pipe(uint64_t *sink, uint32_t mult, int
                 if (V == V_MIX_LO_IADD) {
                     asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(s[i]), "r"(mult));
                     asm volatile("add.u32 %0, %0, %1;" : "+r"(s[i]) : "r"(a[i]));
+                }
+                if (V == V_IND_WIDE_2LOP || V == V_IND_WIDE_4LOP) {
+                    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[i]) : "r"(hi0), "r"(mult));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(a[i]) : "r"(s[i]), "r"(mult));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(s[i]) : "r"(a[i]), "r"(mult));
+                    if (V == V_IND_WIDE_4LOP) {
+                        asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(a[i]) : "r"(s[i]), "r"(mult));
+                        asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(s[i]) : "r"(a[i]), "r"(mult));
+                    }
+                }
+                if (V == V_IND_WIDEC_2LOP) {
+                    uint32_t lo = lo0, hi = hi0;
+                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                                 : "+r"(lo), "+r"(hi) : "r"(hi0), "r"(mult));
+                    acc[i] = ((uint64_t)hi << 32) | lo;
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(a[i]) : "r"(s[i]), "r"(mult));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(s[i]) : "r"(a[i]), "r"(mult));
+                }
+                if (V == V_IND_LO_2LOP) {
+                    uint32_t lo = lo0;
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo) : "r"(mult), "r"(hi0));
+                    acc[i] = ((uint64_t)hi0 << 32) | lo;
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(a[i]) : "r"(s[i]), "r"(mult));
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x56;" : "+r"(s[i]) : "r"(a[i]), "r"(mult));
                 }
                 if (V == V_DFMA || V == V_MIX_WIDE_DFMA) {
                     asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(df[i]) : "d"(dm), "d"(da));
