@@ -296,6 +296,27 @@ __global__ void __launch_bounds__(256) k_push(const __grid_constant__ PushArgs a
     }
 }
 
+// variant: every CTA streams to ONE destination (CTA c: peer c % ndst, slice c / ndst of the block), so a link sees
+// sequential 512-byte bursts from an SM instead of every SM rotating over all peers (SA_PUSH_MODE=1)
+__global__ void __launch_bounds__(256) k_push_per_peer(const __grid_constant__ PushArgs a, const uint4 *src, size_t n16) {
+    const int peer = blockIdx.x % a.ndst;
+    const size_t part = blockIdx.x / a.ndst, nparts = gridDim.x / a.ndst;
+    uint4 *dst = a.dst[0];
+#pragma unroll
+    for (int p = 1; p < TILE_MAX_PEERS; p++)
+        if (p == peer) dst = a.dst[p];
+    const size_t stride = nparts * blockDim.x;
+    size_t i = part * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldcs(src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++) dst[i + u * stride] = v[u];
+    }
+    for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
+}
+
 // ---- subproduct tree over a domain of k points (fast_zerofier / fast_interpolate, ntt.py:66-130) ----
 // The k points sit in the first k of K = 2^ceil(log2 k) leaf slots.  Level j has K >> j nodes of
 // m = 2^j coefficients each, stored back to back.  A node whose leaf range lies completely inside the
@@ -1129,6 +1150,16 @@ int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *st
     const size_t n16 = bytes / 16;
     size_t grid = (n16 + 255) / 256;
     if (grid > (size_t)ctas) grid = (size_t)ctas;
+    static const int mode = [] {
+        const char *e = getenv("SA_PUSH_MODE");
+        return e ? atoi(e) : 0;
+    }();
+    if (mode == 1 && grid >= (size_t)ndst) {
+        grid -= grid % (size_t)ndst;
+        k_push_per_peer<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, (const uint4 *)src, n16);
+        SA_LAUNCH_CHECK();
+        return SA_OK;
+    }
     k_push<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, (const uint4 *)src, n16);
     SA_LAUNCH_CHECK();
     return SA_OK;

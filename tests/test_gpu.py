@@ -242,6 +242,29 @@ def test_peer_buffers_single_process(eng):
         assert (got[o:o + n + 5] == want[:n + 5]).all() and (got[o + n + 5:o + n + 8] == 0).all()
     with pytest.raises(AssertionError, match="unsupported size"):
         eng._check(eng.lib.sa_push(dsts, 3, ptrs[0], 24, eng._stream()))
+    # the one-destination-per-CTA variant of the push kernel (SA_PUSH_MODE=1, read once per process)
+    import subprocess
+    import sys
+    code = r'''
+import sys, ctypes
+sys.path[:0] = [%r]
+import torch, sa_engine
+eng = sa_engine.get_engine()
+for n in (1000, 70001):
+    src = torch.randint(0, 1 << 62, (n, 2), dtype=torch.int64, device=eng.device)
+    dst = torch.zeros((7 * (n + 3), 2), dtype=torch.int64, device=eng.device)
+    for nd in (1, 3, 7):
+        dst.zero_()
+        ptrs = (ctypes.c_void_p * nd)(*[dst.data_ptr() + 16 * (n + 3) * i for i in range(nd)])
+        eng._check(eng.lib.sa_push(ptrs, nd, src.data_ptr(), 16 * n, eng._stream()))
+        for i in range(7):
+            blk = dst[(n + 3) * i:(n + 3) * (i + 1)]
+            assert bool((blk[:n] == src).all()) == (i < nd) and int(blk[n:].abs().sum()) == 0
+print("PUSH_MODE1_OK")
+''' % os.path.join(ROOT_DIR, "stark-anatomy_b200")
+    out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=300,
+                         env=dict(os.environ, SA_PUSH_MODE="1"))
+    assert "PUSH_MODE1_OK" in out.stdout, out.stdout[-500:] + out.stderr[-2000:]
     full = sa_dist.sharded_ntt(up(eng, x), 12, w, assemble="p2p-store", peers=pb)  # world 1: plain transform
     assert (down(eng, full) == want).all()
     pb.close()
