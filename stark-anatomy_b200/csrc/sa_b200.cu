@@ -317,6 +317,56 @@ __global__ void __launch_bounds__(256) k_push_per_peer(const __grid_constant__ P
     for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
 }
 
+// variant: the TMA engine moves the data (SA_PUSH_MODE=2).  One thread per CTA: bulk-async load of a 16 KB chunk
+// into shared memory (mbarrier), then one bulk-async STORE of the chunk per destination (cp.async.bulk shared ->
+// global, bulk groups); two buffers, so the stores of chunk i drain while chunk i + 1 loads.  Costs the SMs a few
+// instructions per 16 KB and destination, which leaves their issue slots to the transform that runs beside it.
+constexpr uint32_t PUSH_TMA_CHUNK = 16384;
+__global__ void __launch_bounds__(32) k_push_tma(const __grid_constant__ PushArgs a, const char *src, size_t bytes) {
+    __shared__ __align__(128) unsigned char buf[2][PUSH_TMA_CHUNK];
+    __shared__ __align__(8) uint64_t bar[2];
+    if (threadIdx.x != 0) return;
+    const uint32_t bar_a[2] = {(uint32_t)__cvta_generic_to_shared(&bar[0]), (uint32_t)__cvta_generic_to_shared(&bar[1])};
+    const uint32_t buf_a[2] = {(uint32_t)__cvta_generic_to_shared(&buf[0][0]), (uint32_t)__cvta_generic_to_shared(&buf[1][0])};
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a[0]));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a[1]));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const size_t nchunks = (bytes + PUSH_TMA_CHUNK - 1) / PUSH_TMA_CHUNK;
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
+        const int sl = it & 1;
+        const size_t off = c * PUSH_TMA_CHUNK;
+        const uint32_t sz = (uint32_t)((bytes - off) < PUSH_TMA_CHUNK ? (bytes - off) : PUSH_TMA_CHUNK);
+        // the stores issued two chunks ago read this buffer: all but the newest group must be done reading
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a[sl]), "r"(sz) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a[sl]),
+                     "l"(src + off), "r"(sz), "r"(bar_a[sl])
+                     : "memory");
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "PUSH_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra PUSH_DONE_%=;\n\t"
+            "bra PUSH_WAIT_%=;\n\t"
+            "PUSH_DONE_%=:\n\t"
+            "}" ::"r"(bar_a[sl]),
+            "r"(phase[sl])
+            : "memory");
+        phase[sl] ^= 1u;
+#pragma unroll
+        for (int p = 0; p < TILE_MAX_PEERS; p++)
+            if (p < a.ndst)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((char *)a.dst[p] + off),
+                             "r"(buf_a[sl]), "r"(sz)
+                             : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- subproduct tree over a domain of k points (fast_zerofier / fast_interpolate, ntt.py:66-130) ----
 // The k points sit in the first k of K = 2^ceil(log2 k) leaf slots.  Level j has K >> j nodes of
 // m = 2^j coefficients each, stored back to back.  A node whose leaf range lies completely inside the
@@ -1154,6 +1204,14 @@ int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *st
         const char *e = getenv("SA_PUSH_MODE");
         return e ? atoi(e) : 0;
     }();
+    if (mode == 2) {
+        size_t g = (bytes + PUSH_TMA_CHUNK - 1) / PUSH_TMA_CHUNK;
+        const size_t cap = (size_t)ctas * 4;  // one-warp CTAs with 32 KB of shared memory: several per SM
+        if (g > cap) g = cap;
+        k_push_tma<<<(unsigned)g, 32, 0, (cudaStream_t)stream>>>(a, (const char *)src, bytes);
+        SA_LAUNCH_CHECK();
+        return SA_OK;
+    }
     if (mode == 1 && grid >= (size_t)ndst) {
         grid -= grid % (size_t)ndst;
         k_push_per_peer<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, (const uint4 *)src, n16);

@@ -242,7 +242,7 @@ def test_peer_buffers_single_process(eng):
         assert (got[o:o + n + 5] == want[:n + 5]).all() and (got[o + n + 5:o + n + 8] == 0).all()
     with pytest.raises(AssertionError, match="unsupported size"):
         eng._check(eng.lib.sa_push(dsts, 3, ptrs[0], 24, eng._stream()))
-    # the one-destination-per-CTA variant of the push kernel (SA_PUSH_MODE=1, read once per process)
+    # the other variants of the push kernel (SA_PUSH_MODE, read once per process): 1 = one destination per CTA
     import subprocess
     import sys
     code = r'''
@@ -262,9 +262,10 @@ for n in (1000, 70001):
             assert bool((blk[:n] == src).all()) == (i < nd) and int(blk[n:].abs().sum()) == 0
 print("PUSH_MODE1_OK")
 ''' % os.path.join(ROOT_DIR, "stark-anatomy_b200")
-    out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=300,
-                         env=dict(os.environ, SA_PUSH_MODE="1"))
-    assert "PUSH_MODE1_OK" in out.stdout, out.stdout[-500:] + out.stderr[-2000:]
+    for push_mode in ("1", "2"):  # 2 = the TMA variant (bulk-async load to shared memory, one bulk store per peer)
+        out = subprocess.run([sys.executable, "-c", code], text=True, capture_output=True, timeout=300,
+                             env=dict(os.environ, SA_PUSH_MODE=push_mode))
+        assert "PUSH_MODE1_OK" in out.stdout, push_mode + out.stdout[-500:] + out.stderr[-2000:]
     full = sa_dist.sharded_ntt(up(eng, x), 12, w, assemble="p2p-store", peers=pb)  # world 1: plain transform
     assert (down(eng, full) == want).all()
     pb.close()
