@@ -78,7 +78,10 @@ class DeviceCodeword:
         eng = sa_engine.get_engine()
         tree = self.device_tree()
         n = self._len
-        if n <= SMALL_TREE and hasattr(eng, "download_tree"):
+        # one index at a time (code/fast_stark.py:162-174 opens 1024 positions one by one): fetch a small tree once
+        # and read the paths on the host; a batch of indices (Fri.query) is one gather on the device
+        indices = list(indices)
+        if n <= SMALL_TREE and hasattr(eng, "download_tree") and (self._host_tree is not None or len(indices) <= 2):
             if self._host_tree is None:
                 self._host_tree = eng.download_tree(tree)
             host, depth = self._host_tree, n.bit_length() - 1
@@ -88,7 +91,7 @@ class DeviceCodeword:
                 node = n + i
                 out.append([bytes(host[(node >> l) ^ 1]) for l in range(depth)])
             return out
-        return eng.merkle_open(tree, list(indices))
+        return eng.merkle_open(tree, indices)
 
     # ---------------------------------------------------------------------------- element access
     def _field_of(self):
