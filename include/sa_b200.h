@@ -72,6 +72,12 @@ int sa_ntt(void *out, const void *in, int log_n, const uint64_t root[2], int inv
  * (a barrier across the ranks after the stream has drained).                                  */
 int sa_ntt_multi(void *const *outs, int nouts, size_t out_offset, const void *in, int log_n,
                  const uint64_t root[2], int inverse, size_t batch, void *stream);
+/* The same through ONE multicast address (NVLS: a multicast object that every rank's buffer is bound to, e.g.
+ * torch.distributed._symmetric_memory's multicast_ptr): the last pass issues multimem.st, one store leaves the
+ * GPU and the NVSwitch delivers it to every rank's buffer, the own one included.  `local` is this rank's own
+ * buffer (same layout; intermediates of the three-pass sizes go there), log_n >= 1.                          */
+int sa_ntt_mcast(void *mc, void *local, size_t out_offset, const void *in, int log_n, const uint64_t root[2],
+                 int inverse, size_t batch, void *stream);
 /* Buffers shared between the processes of one box (one process per GPU): sa_peer_alloc = cudaMalloc (zeroed) +
  * CUDA IPC handle (64 bytes, to be sent to the other processes, e.g. with all_gather_object); sa_peer_open maps
  * another process's buffer into the address space of the CURRENT device and enables peer access to its owner
@@ -87,6 +93,8 @@ int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream);
  * destination.  The push half of sa_dist's "p2p-push" assembly: transform i is pushed on a side stream while
  * transform i + 1 computes.  SA_PUSH_CTAS = CTAs of the push kernel (default 148).                          */
 int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *stream);
+/* The same through ONE multicast address (see sa_ntt_mcast): one multimem.st per 16 bytes, the NVSwitch replicates. */
+int sa_push_mcast(void *mc_dst, const void *src, size_t bytes, void *stream);
 /* Lets kernels of the CURRENT device store to memory of `peer_device` that is mapped into this process
  * (cudaDeviceEnablePeerAccess; fine if it already is enabled).  A buffer opened from an IPC handle belongs to
  * its owner's device ordinal in this process, and opening it under that ordinal does not enable access from

@@ -62,6 +62,7 @@ inline void ntt_fill_common(TileArgs &a) {
     a.twb = nullptr;
     a.twb_stride = 0;
     a.npeer = 0;
+    a.mc_out = nullptr;
 }
 // three-pass split (see the header comment).  tmp: n * batch workspace; out doubles as the first
 // intermediate (a tile reads all of its elements before it writes them, so in == out is fine).

@@ -53,6 +53,9 @@ struct TileArgs {
     // on every rank while it is being computed and no gather pass follows
     fe *peer_out[TILE_MAX_PEERS];
     int npeer;
+    // ... or ONE multicast address (NVLink SHARP / NVLS: a multicast object with every rank's buffer bound to it):
+    // a single multimem.st leaves the GPU and the switch delivers it to every rank's buffer, the own one included
+    fe *mc_out;
 };
 
 // kernel variants: with TF_DYNAMIC everything is decided at run time (partial tiles, optional
@@ -170,6 +173,17 @@ SA_HD fe tile_ldg(const fe *p) {
 SA_HD void tile_st(fe *p, const fe &x) {
 #if defined(__CUDA_ARCH__)
     *reinterpret_cast<uint4 *>(p) = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+#else
+    *p = x;
+#endif
+}
+
+// 16-byte store through a multicast address (sm_90+: multimem.st; the f32 type only names the vector shape)
+SA_HD void tile_st_multicast(fe *p, const fe &x) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(x.v[0])),
+                 "f"(__uint_as_float(x.v[1])), "f"(__uint_as_float(x.v[2])), "f"(__uint_as_float(x.v[3]))
+                 : "memory");
 #else
     *p = x;
 #endif
@@ -305,10 +319,16 @@ SA_HD void ntt_tile_last_stage(int t, fe *sm, const TileArgs &a, long long b, in
             if (use_twb && active) v = fe_montmul(v, tile_ldg(twb + o * twb_sr));
             if (use_scale) v = fe_montmul(v, a.scale);
             if (active) {
-                tile_st(dst + o * out_sr, v);
                 if constexpr ((FLAGS & TF_PEERS) != 0) {
                     const long long rel = (dst - a.out) + (long long)(o * out_sr);
-                    for (int pi = 0; pi < a.npeer; pi++) tile_st(a.peer_out[pi] + rel, v);
+                    if (a.mc_out != nullptr) {
+                        tile_st_multicast(a.mc_out + rel, v);
+                    } else {
+                        tile_st(dst + o * out_sr, v);
+                        for (int pi = 0; pi < a.npeer; pi++) tile_st(a.peer_out[pi] + rel, v);
+                    }
+                } else {
+                    tile_st(dst + o * out_sr, v);
                 }
             }
         }
@@ -336,7 +356,7 @@ template <int LOGL, int ELOG, int C>
 SA_HD int tile_variant(const TileArgs &a) {
     using P = TilePlan<LOGL, ELOG, C>;
     const long long tiles = (long long)((a.ncols + C - 1) / C) * a.nbatch;
-    const int peers = a.npeer > 0 ? TF_PEERS : 0;
+    const int peers = (a.npeer > 0 || a.mc_out != nullptr) ? TF_PEERS : 0;
     if (LOGL < 5 || a.ncols % C != 0 || tiles % P::TPC != 0 || a.has_scale) return TF_DYNAMIC | peers;
     if (peers) return a.twb == nullptr ? (TF_FULL | TF_PEERS) : (TF_DYNAMIC | TF_PEERS);
     return TF_FULL | (a.twb != nullptr ? TF_TWB : 0);

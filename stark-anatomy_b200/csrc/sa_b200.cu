@@ -296,6 +296,21 @@ __global__ void __launch_bounds__(256) k_push(const __grid_constant__ PushArgs a
     }
 }
 
+// variant: ONE multimem.st per 16 bytes through a multicast address (NVLS): the store leaves this GPU once and the
+// NVSwitch replicates it into every rank's buffer bound to the multicast object (sa_push_mcast)
+__global__ void __launch_bounds__(256) k_push_mcast(fe *mc, const fe *src, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        fe v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = tile_ld(src + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++) tile_st_multicast(mc + i + u * stride, v[u]);
+    }
+    for (; i < n16; i += stride) tile_st_multicast(mc + i, tile_ld(src + i));
+}
+
 // variant: every CTA streams to ONE destination (CTA c: peer c % ndst, slice c / ndst of the block), so a link sees
 // sequential 512-byte bursts from an SM instead of every SM rotating over all peers (SA_PUSH_MODE=1)
 __global__ void __launch_bounds__(256) k_push_per_peer(const __grid_constant__ PushArgs a, const uint4 *src, size_t n16) {
@@ -1050,7 +1065,7 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
             const char *e = getenv("SA_NTT_PEER_C");
             return e ? atoi(e) : 8;
         }();
-        if (a.npeer > 0 && peer_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
+        if ((a.npeer > 0 || a.mc_out != nullptr) && peer_c == 8) return launch_tile<LOGL, 4, 8>(a, st);
         return launch_tile<LOGL, 4, 4>(a, st);
     }
     return launch_tile<LOGL, 4, 8>(a, st);
@@ -1083,7 +1098,7 @@ uint64_t sa_launch_count(void) { return g_launches.load(); }
 // the transform proper; `peers` (npeer <= TILE_MAX_PEERS) are extra destinations of the LAST pass: the
 // same element offsets as `out`, in other GPUs' memory (sa_ntt_multi)
 static int ntt_run(void *out, const void *in, int log_n, const uint64_t root[2], int inverse, size_t batch,
-                   cudaStream_t st, fe *const *peers, int npeer) {
+                   cudaStream_t st, fe *const *peers, int npeer, fe *mc = nullptr) {
     if (log_n < 0 || log_n > NTT_MAX_LOG_N) return SA_ESIZE;
     if (batch == 0) return SA_OK;
     const size_t n = size_t(1) << log_n;
@@ -1091,6 +1106,7 @@ static int ntt_run(void *out, const void *in, int log_n, const uint64_t root[2],
         if (out != in) SA_CUDA(cudaMemcpyAsync(out, in, 16 * batch, cudaMemcpyDeviceToDevice, st));
         for (int i = 0; i < npeer; i++)
             SA_CUDA(cudaMemcpyAsync(peers[i], in, 16 * batch, cudaMemcpyDeviceToDevice, st));
+        if (mc) return SA_ESIZE;  // (no kernel runs for length-1 transforms: not offered through a multicast address)
         return SA_OK;
     }
     PlanPtr p;  // keeps the tables alive until the launches below are enqueued (cudaFree waits for them)
@@ -1101,6 +1117,7 @@ static int ntt_run(void *out, const void *in, int log_n, const uint64_t root[2],
     auto with_peers = [&](TileArgs &t) {
         t.npeer = npeer;
         for (int i = 0; i < npeer; i++) t.peer_out[i] = peers[i];
+        t.mc_out = mc;
     };
     if (log_n <= 10) {
         // every transform is one tile column; in-place is safe because a tile reads all of
@@ -1183,6 +1200,13 @@ int sa_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
     return SA_OK;
 }
 
+int sa_ntt_mcast(void *mc, void *local, size_t out_offset, const void *in, int log_n, const uint64_t root[2],
+                 int inverse, size_t batch, void *stream) {
+    if (!mc || !local) return SA_ESIZE;
+    return ntt_run((fe *)local + out_offset, in, log_n, root, inverse, batch, (cudaStream_t)stream, nullptr, 0,
+                   (fe *)mc + out_offset);
+}
+
 int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *stream) {
     if (ndst < 0 || ndst > TILE_MAX_PEERS || (bytes & 15) || (((uintptr_t)src) & 15)) return SA_ESIZE;
     if (ndst == 0 || bytes == 0) return SA_OK;
@@ -1219,6 +1243,21 @@ int sa_push(void *const *dsts, int ndst, const void *src, size_t bytes, void *st
         return SA_OK;
     }
     k_push<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, (const uint4 *)src, n16);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+}
+
+int sa_push_mcast(void *mc_dst, const void *src, size_t bytes, void *stream) {
+    if (!mc_dst || (bytes & 15) || (((uintptr_t)src) & 15) || (((uintptr_t)mc_dst) & 15)) return SA_ESIZE;
+    if (bytes == 0) return SA_OK;
+    static const int ctas = [] {
+        const char *e = getenv("SA_PUSH_CTAS");
+        return e && atoi(e) > 0 ? atoi(e) : 148;
+    }();
+    const size_t n16 = bytes / 16;
+    size_t grid = (n16 + 255) / 256;
+    if (grid > (size_t)ctas) grid = (size_t)ctas;
+    k_push_mcast<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((fe *)mc_dst, (const fe *)src, n16);
     SA_LAUNCH_CHECK();
     return SA_OK;
 }

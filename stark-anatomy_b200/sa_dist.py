@@ -3,7 +3,7 @@
 The hot path shards at batch level: independent transforms (one per polynomial / register /
 column) and independent FRI instances have no data dependence, so every rank (one process per
 GPU, ``torch.distributed``) runs its slice of the batch with no communication during compute.
-What is left is ASSEMBLY: the caller wants the transformed batch on every rank.  Four ways to do
+What is left is ASSEMBLY: the caller wants the transformed batch on every rank.  Several ways to do
 it, all bit-exact (``assemble=`` of ``sharded_ntt``):
 
   "p2p-store"  the product.  Every rank maps the other ranks' output buffers into its own device's address
@@ -13,6 +13,9 @@ it, all bit-exact (``assemble=`` of ``sharded_ntt``):
   "p2p-push"   transforms go to the local buffer; as soon as transform i is done ONE push kernel (``sa_push``:
                one read, a fully coalesced store per peer) sends it to all peers on a high-priority side
                stream while transform i+1 computes.
+  "nvls-store" / "nvls-push"  the same two with ONE multicast address instead of 7 peer addresses (``McastBuffers``
+               over an NVLS multicast object, ``sa_ntt_mcast`` / ``sa_push_mcast``): a store leaves the GPU once and
+               the NVSwitch replicates it to every rank.
   "p2p-copy"   the same with the copy engines (one ``cudaMemcpyAsync`` and stream per peer).
   "nccl-pipelined"  cyclic ownership (rank r owns transforms r, r + world, ...), so chunk i of every rank
                is one in-place ``all_gather_into_tensor`` that runs on a side stream under chunk i+1.
@@ -141,6 +144,67 @@ class PeerBuffers:
         self._own = []
 
 
+class McastBuffers:
+    """``count`` symmetric buffers of ``nelems`` field elements bound to an NVLS multicast object.
+
+    ``torch.distributed._symmetric_memory`` does the plumbing (cuMemCreate + handle exchange + cuMulticastCreate /
+    cuMulticastBindMem): ``local[k]`` is this rank's k-th buffer, ``mc[k]`` the multicast address of the k-th
+    buffer set -- a store to ``mc[k] + off`` leaves this GPU ONCE and the NVSwitch writes it at ``off`` of every
+    rank's buffer, this rank's included.  Raises if the box has no multicast support (no NVSwitch / driver without
+    fabric support); callers fall back to ``PeerBuffers``.  Same ``next`` / ``fence`` / ``close`` protocol.
+    """
+
+    def __init__(self, nelems, group=None, count=2):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        dist = _dist()
+        if dist is None:
+            raise RuntimeError("McastBuffers needs an initialised process group")
+        eng = sa_engine.get_engine()
+        self.eng, self.group, self.nelems = eng, group, nelems
+        self.rank, self.world = _rank_world(group)
+        grp = group if group is not None else dist.group.WORLD
+        self.local, self.mc, self.ptrs, self._handles = [], [], [], []
+        for _ in range(count):
+            t = symm.empty((nelems, 2), dtype=torch.int64, device=eng.device)
+            hdl = symm.rendezvous(t, grp)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mc == 0:
+                raise RuntimeError("no multicast (NVLS) support on this box: symmetric memory has no multicast_ptr")
+            t.zero_()
+            self.local.append(t)
+            self.mc.append(mc)
+            self.ptrs.append([int(x) for x in hdl.buffer_ptrs])
+            self._handles.append(hdl)
+        self.turn = 0
+        self.flag = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        self._push = None
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def next(self):
+        """(local buffer as a tensor, multicast address of the same buffer set) of this call"""
+        k = self.turn
+        self.turn = (self.turn + 1) % len(self.local)
+        return self.local[k], self.mc[k]
+
+    def fence(self):
+        if self.world > 1:
+            _dist().all_reduce(self.flag, group=self.group)
+
+    def push_stream(self):
+        import torch
+        if self._push is None:
+            self._push = torch.cuda.Stream(priority=-1)
+        return self._push
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        _dist().barrier(group=self.group)
+        self.local, self.mc, self.ptrs, self._handles = [], [], [], []
+
+
 # ------------------------------------------------------------------------------- sharded transforms
 def owner_cyclic(b, world):
     return b % world
@@ -171,11 +235,20 @@ def sharded_ntt(vectors, log_n, root, inverse=False, gather=True, group=None, as
     if assemble == "nccl-pipelined":
         return _ntt_nccl_pipelined(eng, vectors, log_n, root, inverse, n, per, rank, world, group)
     if peers is None:
-        raise ValueError("assemble=%r needs peers=PeerBuffers(batch * n)" % assemble)
+        raise ValueError("assemble=%r needs peers=PeerBuffers(batch * n) / McastBuffers(batch * n)" % assemble)
     lo = rank * per
     mine = eng.slice(vectors, lo * n, (lo + per) * n)
     local, bufs = peers.next()
-    if assemble == "p2p-store":
+    if assemble in ("nvls-store", "nvls-push"):
+        if not isinstance(peers, McastBuffers):
+            raise ValueError("assemble=%r needs peers=McastBuffers(batch * n)" % assemble)
+        if assemble == "nvls-store":
+            eng.ntt_mcast(bufs, local, lo * n, mine, log_n, root, inverse=inverse, batch=per)
+        else:
+            _ntt_mcast_push(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, lo)
+    elif not isinstance(peers, PeerBuffers):
+        raise ValueError("assemble=%r needs peers=PeerBuffers(batch * n)" % assemble)
+    elif assemble == "p2p-store":
         outs = [bufs[rank]] + [bufs[q] for q in range(world) if q != rank]
         eng.ntt_multi(outs, lo * n, mine, log_n, root, inverse=inverse, batch=per)
     elif assemble == "p2p-copy":
@@ -225,6 +298,23 @@ def _ntt_p2p_push(eng, peers, local, bufs, mine, log_n, root, inverse, n, per, l
         off = 16 * (lo + i) * n
         dsts = (ctypes.c_void_p * len(others))(*[bufs[q] + off for q in others])
         eng._check(eng.lib.sa_push(dsts, len(others), bufs[rank] + off, 16 * n, ctypes.c_void_p(side.cuda_stream)))
+    main.wait_stream(side)
+
+
+def _ntt_mcast_push(eng, peers, local, mc, mine, log_n, root, inverse, n, per, lo):
+    import ctypes
+    import torch
+    side = peers.push_stream()
+    main = torch.cuda.current_stream()
+    for i in range(per):
+        dst = local[(lo + i) * n:(lo + i + 1) * n]
+        eng.ntt_into(dst, mine[i * n:(i + 1) * n], log_n, root, inverse=inverse)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        off = 16 * (lo + i) * n  # one multimem store per 16 bytes: the switch delivers it to every rank
+        eng._check(eng.lib.sa_push_mcast(ctypes.c_void_p(mc + off), ctypes.c_void_p(dst.data_ptr()), 16 * n,
+                                         ctypes.c_void_p(side.cuda_stream)))
     main.wait_stream(side)
 
 

@@ -37,6 +37,8 @@ SYMBOLS = [
     ("sa_launch_count", ctypes.c_uint64, []),
     ("sa_ntt", _ci, [_vp, _vp, _ci, _u64p, _ci, _sz, _vp]),
     ("sa_ntt_multi", _ci, [ctypes.POINTER(ctypes.c_void_p), _ci, _sz, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_ntt_mcast", _ci, [_vp, _vp, _sz, _vp, _ci, _u64p, _ci, _sz, _vp]),
+    ("sa_push_mcast", _ci, [_vp, _vp, _sz, _vp]),
     ("sa_enable_peer_access", _ci, [_ci]),
     ("sa_peer_alloc", _ci, [ctypes.POINTER(ctypes.c_void_p), _sz, ctypes.c_char_p]),
     ("sa_peer_open", _ci, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
@@ -192,6 +194,13 @@ class CudaEngine:
         ptrs = (ctypes.c_void_p * len(outs))(*[int(t) if isinstance(t, int) else int(t.data_ptr()) for t in outs])
         self._check(self.lib.sa_ntt_multi(ptrs, len(outs), out_offset, vec.data_ptr(), log_n, _limbs(root),
                                           int(bool(inverse)), batch, self._stream()))
+
+    def ntt_mcast(self, mc_ptr, local, out_offset, vec, log_n, root, inverse=False, batch=1):
+        """sa_ntt_mcast: transform `vec`, store the result through the multicast address `mc_ptr` (every rank's
+        buffer receives it, this rank's `local` included) at element offset `out_offset`"""
+        vec = vec.contiguous()
+        self._check(self.lib.sa_ntt_mcast(ctypes.c_void_p(int(mc_ptr)), local.data_ptr(), out_offset, vec.data_ptr(),
+                                          log_n, _limbs(root), int(bool(inverse)), batch, self._stream()))
 
     def wrap_pointer(self, ptr, nelems):
         """a device vector (torch.int64[n, 2]) over memory this process got from the C library"""

@@ -43,9 +43,17 @@ try:
 except Exception as exc:
     peers = None
     report["peer_buffers_error"] = repr(exc)[:400]
-MODES = os.environ.get("SA_DIST_MODES", "nccl,nccl-pipelined,p2p-copy,p2p-store,p2p-push").split(",")
+MODES = os.environ.get("SA_DIST_MODES", "nccl,nccl-pipelined,p2p-copy,p2p-store,p2p-push,nvls-store,nvls-push").split(",")
+mcast = None
+if any(m.startswith("nvls") for m in MODES):
+    try:
+        mcast = sa_dist.McastBuffers(batch * n)
+    except Exception as exc:
+        report["mcast_buffers_error"] = repr(exc)[:400]
+all_peers = peers
 for mode in MODES:  # (the plain ones first: a fault in a peer mode cannot hide them)
-    if mode.startswith("p2p") and peers is None:
+    peers = mcast if mode.startswith("nvls") else all_peers
+    if mode.startswith(("p2p", "nvls")) and peers is None:
         continue
     try:
         for _ in range(3):
