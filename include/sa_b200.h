@@ -124,6 +124,13 @@ int sa_scale(void *out, const void *in, size_t n, const uint64_t factor[2], void
  * out[j] = sum_i coeffs[i] * points[j]^i                                                 */
 int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
                  void *stream);
+/* The same with the algorithm chosen by the caller: mode 0 = what sa_poly_eval does (Horner, one thread per
+ * point, below 2^27.5 coefficient-point products; above that the walk down the subproduct tree of the points,
+ * max(ncoef, npoints) <= 2^20), 1 = Horner, 2 = the tree walk (ncoef, npoints >= 1).  The reference walks down a
+ * remainder tree (ntt.py:82-100); the device walks down the TRANSPOSED interpolation tree (no divisions): one
+ * power-series inverse at the root, then one batched transform pair per level.  Same values.                 */
+int sa_poly_eval_mode(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints, int mode,
+                      void *stream);
 
 /* code/ntt.py:66-80 fast_zerofier: out[0..k] = coefficients of prod_i (X - domain[i]) (monic,
  * k + 1 coefficients), k <= 2^20.  Small domains: one kernel; larger ones: the subproduct tree of

@@ -460,6 +460,80 @@ __global__ void k_tree_root(fe *out, const fe *root, long long k, long long K) {
     if (i <= k) tile_st(out + i, (i == K) ? fe_one() : tile_ld(root + i));
 }
 
+// ---- multi-point evaluation over the same tree (fast_evaluate, ntt.py:82-100, and M'(d_i) of fast_interpolate) ----
+// The reference walks DOWN a remainder tree (f mod left zerofier, f mod right zerofier, ...).  Here the walk down is
+// the TRANSPOSE of the interpolation up-sweep (Bostan-Lecerf-Schost): the up-sweep q -> P = sum q_i M / (X - d_i) is
+// linear, rev(P) / rev(M) = sum q_i / (1 - d_i x) has the power sums sum_i q_i d_i^j as coefficients, i.e.
+// (transposed Vandermonde) = (multiply by alpha = 1 / rev(M) mod x^n) o (reverse) o (up-sweep), so
+//   f(d_i) = (up-sweep)^T [ (rev(f) * alpha mod x^n) shifted ],
+// and the transposed up-sweep turns every product P_L * M_R into a CORRELATION with M_R: with the node transforms
+// kept from the build, c_L = IDFT(DFT(c_node)[t] * DFT(M_R)[-t])[0..m) (+ c_node[m..2m) for the implied leading 1 of
+// a full M_R), c_R likewise with M_L.  No division anywhere: one power-series inverse (Newton) at the top, then per
+// level one batched forward transform, one pointwise kernel, one batched inverse transform, one fix-up.
+// W (two blocks of 4s): [0] = rev_k(z) mod x^2s, zero padded; [1] = alpha mod x^s, zero padded.  z has k + 1 coefficients.
+__global__ void k_series_pad(fe *W, const fe *z, long long k, const fe *alpha, long long s) {
+    const long long stride = (long long)gridDim.x * blockDim.x, n4 = 4 * s;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * n4; idx += stride) {
+        const long long t = idx & (n4 - 1);
+        fe v = fe_zero();
+        if (idx < n4) {
+            if (t < 2 * s && t <= k) v = tile_ld(z + (k - t));
+        } else if (t < s) {
+            v = tile_ld(alpha + t);
+        }
+        tile_st(W + idx, v);
+    }
+}
+// Newton step in the transform domain: W[0][t] = a * (2 - r * a), r = W[0][t], a = W[1][t]  (degree < 4s: no wrap)
+__global__ void k_series_step(fe *W, long long n4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const fe two = fe_make(2, 0, 0, 0);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+        const fe r = tile_ld(W + t), a_m = fe_to_mont(tile_ld(W + n4 + t));
+        const fe ra = fe_montmul(a_m, r);  // canonical r * a
+        tile_st(W + t, fe_montmul(a_m, fe_sub(two, ra)));
+    }
+}
+// W (two blocks of n2): [0] = rev_{n-1}(f) (f has nf <= n coefficients), [1] = alpha mod x^n, both zero padded
+__global__ void k_eval_top_pad(fe *W, const fe *f, long long nf, const fe *alpha, long long n, long long n2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * n2; idx += stride) {
+        const long long t = idx & (n2 - 1);
+        fe v = fe_zero();
+        if (idx < n2) {
+            if (t < n && n - 1 - t < nf) v = tile_ld(f + (n - 1 - t));
+        } else if (t < n) {
+            v = tile_ld(alpha + t);
+        }
+        tile_st(W + idx, v);
+    }
+}
+// root vector of the walk down: c[i] = s[n - k + i] for i < k (s = rev(f) * alpha), 0 for the empty slots
+__global__ void k_eval_root(fe *c, const fe *s, long long n, long long k, long long K) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) tile_st(c + i, i < k ? tile_ld(s + (n - k + i)) : fe_zero());
+}
+// O[child][t] = chat[parent][t] * VT[sibling][(2m - t) mod 2m]   (child blocks of 2m; VT = level-mlog transforms)
+__global__ void k_tree_down(fe *O, const fe *chat, const fe *VT, long long K, int mlog) {
+    const long long stride = (long long)gridDim.x * blockDim.x, two_m = 2ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * K; idx += stride) {
+        const long long child = idx >> (mlog + 1), t = idx & (two_m - 1);
+        const fe a = tile_ld(chat + (child >> 1) * two_m + t);
+        const fe b = tile_ld(VT + (child ^ 1) * two_m + ((two_m - t) & (two_m - 1)));
+        tile_st(O + idx, fe_montmul(fe_to_mont(a), b));
+    }
+}
+// next[child][j] = O[child][j] + [sibling full] * cur[parent][m + j],  j < m
+__global__ void k_tree_down_fix(fe *next, const fe *O, const fe *cur, long long K, int mlog, long long k) {
+    const long long stride = (long long)gridDim.x * blockDim.x, m = 1ll << mlog;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < K; idx += stride) {
+        const long long child = idx >> mlog, j = idx & (m - 1);
+        fe v = tile_ld(O + child * 2 * m + j);
+        if (tree_full(child ^ 1, mlog, k)) v = fe_add(v, tile_ld(cur + (child >> 1) * 2 * m + m + j));
+        tile_st(next + idx, v);
+    }
+}
+
 __global__ void k_fri_fold(fe *next, const fe *cw, long long half, const fe *xinv, fe s_m, fe inv2_m) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
@@ -1520,8 +1594,8 @@ int sa_scale(void *out, const void *in, size_t n, const uint64_t factor[2], void
     return SA_OK;
 }
 
-int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
-                 void *stream) {
+static int poly_eval_horner(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints,
+                            void *stream) {
     if (npoints == 0) return SA_OK;
     const int bs = 64;
     k_poly_eval<<<(unsigned)((npoints + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
@@ -1536,12 +1610,17 @@ int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points
 constexpr int TREE_MAX_LOG = 20;  // 2^20 points: ~1 GiB of tree, transforms and scratch
 static int g_zf_direct_max = 512;       // up to here the one-CTA sweep kernel (SA_ZF_DIRECT_MAX with -DSA_TUNE)
 static int g_interp_direct_max = 1024;  // up to here the k x k Lagrange kernels (SA_INTERP_DIRECT_MAX)
+// Horner (one thread per point, ncoef * npoints products) up to this many products, the transposed tree walk above
+// (SA_EVAL_TREE_MIN_LOG = log2 of the product count with -DSA_TUNE).  Measured (profiles/r02p_poly_sweep.jsonl, square
+// jobs): 4096 points Horner 0.50 ms / walk 1.08 ms, 16384 points 2.01 / 1.36 ms, 65536 points 18.9 / 1.80 ms.
+static double g_eval_tree_min = 189812531.0;  // 2^27.5
 static void tree_config() {
 #ifdef SA_TUNE
     static std::once_flag once;
     std::call_once(once, [] {
         if (const char *e = getenv("SA_ZF_DIRECT_MAX")) g_zf_direct_max = atoi(e);
         if (const char *e = getenv("SA_INTERP_DIRECT_MAX")) g_interp_direct_max = atoi(e);
+        if (const char *e = getenv("SA_EVAL_TREE_MIN_LOG")) g_eval_tree_min = ldexp(1.0, atoi(e));
     });
 #endif
 }
@@ -1603,6 +1682,71 @@ static int tree_alloc(PolyTree &t, size_t k, bool keep_transforms, size_t extra_
     t.transforms = keep_transforms ? ws + lv : nullptr;
     t.scratch = ws + lv + tr;
     if (extra) *extra = ws + lv + tr + sc;
+    return SA_OK;
+}
+
+static inline size_t pow2_ceil(size_t x) {
+    size_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+// elements of extra workspace tree_multipoint needs for nf coefficients at the tree's k points
+static size_t multipoint_extra(size_t nf, size_t k) {
+    const size_t N = pow2_ceil(nf > k ? nf : k), K = pow2_ceil(k);
+    return 4 * N + N + 2 * K + 16;
+}
+// vals[i] = f(d_i), i < k, for the tree `t` (built with transforms kept) whose root polynomial is z (k + 1
+// coefficients); f has nf >= 1 coefficients.  `ws` = multipoint_extra(nf, k) elements.  See the kernels' comment.
+static int tree_multipoint(const PolyTree &t, const fe *z, const fe *f, size_t nf, fe *vals, fe *ws, cudaStream_t st) {
+    const long long k = t.k, K = t.K;
+    const long long n = (long long)(nf > (size_t)k ? nf : (size_t)k), N = (long long)pow2_ceil((size_t)n);
+    fe *W = ws, *alpha = W + 4 * N, *c0 = alpha + N, *c1 = c0 + K;
+    int rc;
+    uint64_t root[2];
+    // alpha = 1 / rev_k(z) mod x^N by Newton: alpha_2s = alpha_s (2 - r alpha_s) mod x^2s in transforms of size 4s
+    const fe one = fe_one();
+    SA_CUDA(cudaMemcpyAsync(alpha, &one, sizeof(fe), cudaMemcpyHostToDevice, st));
+    for (long long s = 1; s < N; s <<= 1) {
+        const int lg = host_log2((size_t)(4 * s));
+        tree_root_of_unity(root, lg);
+        k_series_pad<<<tree_grid(8 * s), 256, 0, st>>>(W, z, k, alpha, s);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(W, W, lg, root, 0, 2, st)) != SA_OK) return rc;
+        k_series_step<<<tree_grid(4 * s), 256, 0, st>>>(W, 4 * s);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(W, W, lg, root, 1, 1, st)) != SA_OK) return rc;
+        SA_CUDA(cudaMemcpyAsync(alpha, W, sizeof(fe) * 2 * s, cudaMemcpyDeviceToDevice, st));
+    }
+    // s = rev_{n-1}(f) * alpha mod x^n; the walk starts from c_root[i] = s[n - k + i]
+    {
+        const long long n2 = 2 * N;
+        const int lg = host_log2((size_t)n2);
+        tree_root_of_unity(root, lg);
+        k_eval_top_pad<<<tree_grid(2 * n2), 256, 0, st>>>(W, f, (long long)nf, alpha, n, n2);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(W, W, lg, root, 0, 2, st)) != SA_OK) return rc;
+        k_pointwise_mul<<<tree_grid(n2), 256, 0, st>>>(W, W, W + n2, n2);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(W, W, lg, root, 1, 1, st)) != SA_OK) return rc;
+        k_eval_root<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(c0, W, n, k, K);
+        SA_LAUNCH_CHECK();
+    }
+    // walk down: level j + 1 (nodes of 2m) -> level j (nodes of m); W is free again: chat = W[0, K), O = W[K, 3K)
+    fe *cur = c0, *nxt = c1, *chat = W, *O = W + K;
+    for (int j = t.logK - 1; j >= 0; j--) {
+        tree_root_of_unity(root, j + 1);
+        const fe *VT = t.transforms + (size_t)j * 2 * K;
+        if ((rc = sa_ntt(chat, cur, j + 1, root, 0, (size_t)(K >> (j + 1)), st)) != SA_OK) return rc;
+        k_tree_down<<<tree_grid(2 * K), 256, 0, st>>>(O, chat, VT, K, j);
+        SA_LAUNCH_CHECK();
+        if ((rc = sa_ntt(O, O, j + 1, root, 1, (size_t)(K >> j), st)) != SA_OK) return rc;
+        k_tree_down_fix<<<tree_grid(K), 256, 0, st>>>(nxt, O, cur, K, j, k);
+        SA_LAUNCH_CHECK();
+        fe *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    SA_CUDA(cudaMemcpyAsync(vals, cur, sizeof(fe) * (size_t)k, cudaMemcpyDeviceToDevice, st));
     return SA_OK;
 }
 
@@ -1669,16 +1813,21 @@ static int interpolate_tree(void *out, const void *domain, const void *values, s
     fe *extra = nullptr;
     // extra: z (K + 1) | dz (K) | ev (K) | q (K) | P levels ping-pong (2 * K)
     const size_t Kpad = (size_t)1 << (k <= 1 ? 0 : (64 - __builtin_clzll((unsigned long long)(k - 1))));
-    int rc = tree_alloc(t, k, true, 6 * Kpad + 16, &extra, st);
+    const bool walk = (double)k * (double)k >= g_eval_tree_min;  // M'(d_i): Horner is k^2 products
+    int rc = tree_alloc(t, k, true, 6 * Kpad + 16 + (walk ? multipoint_extra(k, k) : 0), &extra, st);
     if (rc != SA_OK) return rc;
     const size_t K = (size_t)t.K;
-    fe *z = extra, *dz = z + K + 1, *ev = dz + K, *q = ev + K, *Pa = q + K, *Pb = Pa + K;
+    fe *z = extra, *dz = z + K + 1, *ev = dz + K, *q = ev + K, *Pa = q + K, *Pb = Pa + K, *mp = Pb + K + 16;
     if ((rc = tree_build(t, (const fe *)domain, st)) != SA_OK) return rc;
     k_tree_root<<<(unsigned)((k + 1 + 255) / 256), 256, 0, st>>>(z, t.levels + (size_t)t.logK * K, t.k, t.K);
     SA_LAUNCH_CHECK();
     k_derivative<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(dz, z, (long long)k);
     SA_LAUNCH_CHECK();
-    if ((rc = sa_poly_eval(ev, dz, k, domain, k, (void *)st)) != SA_OK) return rc;
+    if (walk)
+        rc = tree_multipoint(t, z, dz, k, ev, mp, st);
+    else
+        rc = poly_eval_horner(ev, dz, k, domain, k, (void *)st);
+    if (rc != SA_OK) return rc;
     if ((rc = sa_pointwise_div(q, values, ev, k, (void *)st)) != SA_OK) return rc;  // SA_EDIVZERO: repeated point
     k_tree_qleaves<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(Pa, q, t.k, t.K);
     SA_LAUNCH_CHECK();
@@ -1710,6 +1859,38 @@ int sa_interpolate(void *out, const void *domain, const void *values, size_t k, 
     if (k <= (size_t)g_interp_direct_max && k <= (size_t)ZF_MAXK) return interpolate_direct(out, domain, values, k, st);
     if (k > ((size_t)1 << TREE_MAX_LOG)) return SA_ESIZE;
     return interpolate_tree(out, domain, values, k, st);
+}
+
+// fast_evaluate (ntt.py:82-100): Horner for small jobs, the transposed tree walk (tree_multipoint) for big ones
+int sa_poly_eval_mode(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints, int mode,
+                      void *stream) {
+    if (npoints == 0) return SA_OK;
+    if (mode < 0 || mode > 2) return SA_ESIZE;
+    tree_config();
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nmax = ncoef > npoints ? ncoef : npoints;
+    if (mode == 0)
+        mode = (ncoef < 2 || npoints < 2 || (double)ncoef * (double)npoints < g_eval_tree_min ||
+                nmax > ((size_t)1 << TREE_MAX_LOG)) ? 1 : 2;
+    if (mode == 1) return poly_eval_horner(out, coeffs, ncoef, points, npoints, stream);
+    if (nmax > ((size_t)1 << TREE_MAX_LOG)) return SA_ESIZE;
+    if (ncoef == 0) {  // the zero polynomial
+        SA_CUDA(cudaMemsetAsync(out, 0, sizeof(fe) * npoints, st));
+        return SA_OK;
+    }
+    PolyTree t;
+    fe *extra = nullptr;
+    const size_t K = pow2_ceil(npoints);
+    int rc = tree_alloc(t, npoints, true, K + 1 + 16 + multipoint_extra(ncoef, npoints), &extra, st);
+    if (rc != SA_OK) return rc;
+    fe *z = extra, *mp = z + K + 1 + 15;
+    if ((rc = tree_build(t, (const fe *)points, st)) != SA_OK) return rc;
+    k_tree_root<<<(unsigned)((npoints + 1 + 255) / 256), 256, 0, st>>>(z, t.levels + (size_t)t.logK * t.K, t.k, t.K);
+    SA_LAUNCH_CHECK();
+    return tree_multipoint(t, z, (const fe *)coeffs, ncoef, (fe *)out, mp, st);
+}
+int sa_poly_eval(void *out, const void *coeffs, size_t ncoef, const void *points, size_t npoints, void *stream) {
+    return sa_poly_eval_mode(out, coeffs, ncoef, points, npoints, 0, stream);
 }
 
 // ---- Merkle / FRI ----

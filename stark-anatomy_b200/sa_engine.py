@@ -53,6 +53,7 @@ SYMBOLS = [
     ("sa_pointwise_div", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_scale", _ci, [_vp, _vp, _sz, _u64p, _vp]),
     ("sa_poly_eval", _ci, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    ("sa_poly_eval_mode", _ci, [_vp, _vp, _sz, _vp, _sz, _ci, _vp]),
     ("sa_zerofier", _ci, [_vp, _vp, _sz, _vp]),
     ("sa_interpolate", _ci, [_vp, _vp, _vp, _sz, _vp]),
     ("sa_merkle_tree", _ci, [_vp, _vp, _sz, _vp]),
@@ -226,11 +227,13 @@ class CudaEngine:
         self._check(self.lib.sa_scale(out.data_ptr(), vec.data_ptr(), vec.shape[0], _limbs(factor), self._stream()))
         return out
 
-    def poly_eval(self, coeffs, points):
+    def poly_eval(self, coeffs, points, mode=0):
+        """values of the polynomial at the points; mode 0 = the library chooses, 1 = Horner kernel, 2 = walk down
+        the subproduct tree of the points (sa_poly_eval_mode)"""
         coeffs, points = coeffs.contiguous(), points.contiguous()
         out = self.empty(points.shape[0])
-        self._check(self.lib.sa_poly_eval(out.data_ptr(), coeffs.data_ptr(), coeffs.shape[0], points.data_ptr(),
-                                          points.shape[0], self._stream()))
+        self._check(self.lib.sa_poly_eval_mode(out.data_ptr(), coeffs.data_ptr(), coeffs.shape[0], points.data_ptr(),
+                                               points.shape[0], int(mode), self._stream()))
         return out
 
     MAX_DIRECT_POINTS = 1 << 20  # sa_zerofier / sa_interpolate handle this many points per call

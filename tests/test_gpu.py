@@ -487,6 +487,40 @@ def test_zerofier_and_interpolate(eng, k):
             eng.interpolate(up(eng, dom), up(eng, vals))
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 8, 9, 17, 100, 256, 257, 513, 1000, 4097])
+def test_poly_eval_tree_walk_matches_oracle(eng, k):
+    """fast_evaluate's values (ntt.py:82-100) through the walk down the subproduct tree (sa_poly_eval_mode 2: the
+    transposed interpolation tree, no divisions) vs the oracle's Horner: full and ragged trees, fewer / as many /
+    more coefficients than points, the zero and constant polynomials, repeated points"""
+    pts = rand_np(300 + k, k)
+    if k >= 3:
+        pts[k - 1] = pts[0]  # a repeated point is fine for evaluation
+    for ncoef in sorted({1, 2, max(1, k - 1), k, k + 7, 3 * k + 1, 1 << (k.bit_length())}):
+        coeffs = rand_np(400 + k + ncoef, ncoef)
+        if ncoef > 2:
+            coeffs[ncoef - 1] = 0  # a leading zero
+        got = down(eng, eng.poly_eval(up(eng, coeffs), up(eng, pts), mode=2))
+        assert (got == O.poly_eval_np(coeffs, pts)).all(), (k, ncoef)
+        assert (got == down(eng, eng.poly_eval(up(eng, coeffs), up(eng, pts), mode=1))).all()
+    zero = np.zeros((5, 2), dtype=np.uint64)
+    assert (down(eng, eng.poly_eval(up(eng, zero), up(eng, pts), mode=2)) == 0).all()
+
+
+@pytest.mark.parametrize("k,ncoef", [(1 << 15, 1 << 15), ((1 << 16) + 12345, 1 << 16), (1 << 14, (1 << 17) + 3),
+                                     (1 << 18, 1 << 18)])
+def test_poly_eval_tree_walk_large(eng, k, ncoef):
+    """the size the library switches to the walk by itself (>= 2^29 coefficient-point products): the walk's values
+    equal the Horner kernel's on a sample of the points and the oracle's on a few"""
+    coeffs, pts = rand_np(500 + k % 89, ncoef), rand_np(501 + k % 89, k)
+    vc, vp = up(eng, coeffs), up(eng, pts)
+    got = eng.poly_eval(vc, vp)  # mode 0: the library's own choice at this size is the walk
+    assert (down(eng, got) == down(eng, eng.poly_eval(vc, vp, mode=2))).all()
+    step = max(1, k // 4096)
+    assert (down(eng, got[::step].contiguous()) == down(eng, eng.poly_eval(vc, vp[::step].contiguous(), mode=1))).all()
+    few = [0, 1, k // 2, k - 1]
+    assert (down(eng, got)[few] == O.poly_eval_np(coeffs, pts[few])).all()
+
+
 @pytest.mark.parametrize("k", [1 << 16, (1 << 16) + 12345, 1 << 18])
 def test_zerofier_and_interpolate_large_by_property(eng, k):
     """one C call each at sizes the oracle's O(k^2) loops cannot reach: the zerofier is monic, vanishes on
@@ -509,9 +543,11 @@ def test_zerofier_and_interpolate_large_by_property(eng, k):
                    inverse=True)
     assert (down(eng, prod)[:k + 1] == zh).all() and (down(eng, prod)[k + 1:] == 0).all()
     if k <= (1 << 16) + 12345:
-        poly = eng.interpolate(vd, up(eng, vals))
+        poly = eng.interpolate(vd, up(eng, vals))  # (M'(d_i) through the walk down the tree at this size)
         assert eng.length(poly) == k
         assert (down(eng, eng.poly_eval(poly, vd)) == vals).all()
+        step = 53  # ... and independently of the walk: the Horner kernel on a sample of the points
+        assert (down(eng, eng.poly_eval(poly, vd[::step].contiguous(), mode=1)) == vals[::step]).all()
 
 
 @pytest.mark.parametrize("log_n", [0, 1, 2, 5, 6, 7, 9, 10, 11, 13, 14, 15, 16, 17, 18])

@@ -12,7 +12,7 @@ import torch  # noqa: E402
 import sa_engine  # noqa: E402
 
 eng = sa_engine.get_engine()
-ks = [int(a) for a in sys.argv[1:]] or [27, 284, 1024, 4096, 1 << 14, 1 << 16, 1 << 18]
+ks = [int(a) for a in sys.argv[1:]] or [27, 284, 1024, 4096, 1 << 14, 1 << 15, 1 << 16, 1 << 18, 1 << 20]
 
 
 def rand(seed, n):
@@ -40,12 +40,18 @@ for k in ks:
     z = eng.zerofier(dom)
     launches_z = eng.launch_count() - l0
     line = {"k": k, "zerofier_ms": timed(lambda: eng.zerofier(dom), reps), "zerofier_launches": launches_z}
-    if k <= 1 << 17:
+    if k <= 1 << 20:
         l0 = eng.launch_count()
         poly = eng.interpolate(dom, vals)
         line["interpolate_launches"] = eng.launch_count() - l0
         line["interpolate_ms"] = timed(lambda: eng.interpolate(dom, vals), reps)
-        line["poly_eval_k_points_ms"] = timed(lambda: eng.poly_eval(poly, dom), reps)
-        ok = bool((eng.poly_eval(poly, dom) == vals).all().item())
+        if k <= 1 << 17:
+            line["poly_eval_horner_ms"] = timed(lambda: eng.poly_eval(poly, dom, mode=1), reps)
+        l0 = eng.launch_count()
+        eng.poly_eval(poly, dom, mode=2)
+        line["poly_eval_walk_launches"] = eng.launch_count() - l0
+        line["poly_eval_walk_ms"] = timed(lambda: eng.poly_eval(poly, dom, mode=2), reps)
+        line["poly_eval_auto_ms"] = timed(lambda: eng.poly_eval(poly, dom), reps)
+        ok = bool((eng.poly_eval(poly, dom, mode=2) == vals).all().item())
         line["interpolant_takes_values"] = ok
     print(json.dumps(line), flush=True)
