@@ -1630,13 +1630,22 @@ static void tree_config() {
 }
 // primitive 2^log-th root of unity: generator^(2^119 / 2^log), algebra.py:100-114
 static void tree_root_of_unity(uint64_t out[2], int log) {
-    // algebra.py:100-102: generator 85408008396924667383611388730472331217 has order 2^119
-    const uint64_t g[2] = {0xb5038f9c18f6f7d1ull, 0x4040fbed12ee470full};
-    fe w = fe_to_mont(fe_from_limbs(g));
-    for (int i = 119; i > log; i--) w = fe_montmul(w, w);
-    const fe c = fe_from_mont(w);
-    out[0] = (uint64_t)c.v[0] | ((uint64_t)c.v[1] << 32);
-    out[1] = (uint64_t)c.v[2] | ((uint64_t)c.v[3] << 32);
+    // algebra.py:100-102: generator 85408008396924667383611388730472331217 has order 2^119; the table is built
+    // once (a tree of 2^16 points asks ~60 times per call, each a chain of up to 118 host-side squarings)
+    static uint64_t table[120][2];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const uint64_t g[2] = {0xb5038f9c18f6f7d1ull, 0x4040fbed12ee470full};
+        fe w = fe_to_mont(fe_from_limbs(g));
+        for (int i = 119; i >= 0; i--) {
+            const fe c = fe_from_mont(w);
+            table[i][0] = (uint64_t)c.v[0] | ((uint64_t)c.v[1] << 32);
+            table[i][1] = (uint64_t)c.v[2] | ((uint64_t)c.v[3] << 32);
+            w = fe_montmul(w, w);
+        }
+    });
+    out[0] = table[log][0];
+    out[1] = table[log][1];
 }
 struct PolyTree {
     int logK = 0;
