@@ -480,6 +480,29 @@ def run_ours(args):
                         "note": "2^20 elements; 'list in' packs 2^20 FieldElement objects and uploads 16 MiB, 'list out' "
                                 "creates 2^20 objects; device lists (sa_devlist.DeviceCodeword) skip both"}
 
+    # ---- SURVEY 8 a4-a6 at 2^16 points, device-resident inputs, one C call each (for the record)
+    poly_ms = None
+    if rank == 0 and world == 1:
+        K16 = 1 << 16
+        dom, pvals = x[:K16].contiguous(), x[K16:2 * K16].contiguous()
+
+        def ev_ms(fn, reps=5):
+            fn()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            for _ in range(reps):
+                r = fn()
+            b_.record(stream)
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / reps, r
+        z_ms, _ = ev_ms(lambda: eng.zerofier(dom))
+        i_ms, poly = ev_ms(lambda: eng.interpolate(dom, pvals))
+        e_ms, back = ev_ms(lambda: eng.poly_eval(poly, dom))
+        assert bool((back == pvals).all().item()), "interpolant does not take the prescribed values"
+        poly_ms = {"points": K16, "fast_zerofier": z_ms, "fast_interpolate": i_ms, "fast_evaluate": e_ms,
+                   "note": "sa_zerofier / sa_interpolate / sa_poly_eval on 2^16 random points: device subproduct tree, "
+                           "walk down the transposed tree; the interpolant is checked against the values"}
+
     # ---- N > 1: the same batch sharded over the ranks WITH the assembly on every rank (every rank takes part)
     with_allgather = allgather_leg(eng, dist, rank, world, w) if dist is not None else None
 
@@ -554,6 +577,7 @@ def run_ours(args):
         "single_ntt_us": single_us,
         "list_api_ntt_2_20_s": list_api_s, "list_api_fri_commit_2_20_s": fri_list_api_s,
         "list_api": list_api_dev,
+        "poly_ops_2_16_ms": poly_ms,
         "fri_commit_ms_2_20": fri_ms, "fri_commit_cpu_port_ms_2_20": fri_cpu_ms,
         "fri_roofline": None if fri_ms is None else {
             "bound": "alu pipe (blake2b: 64-bit add / xor / rotate), not HBM",

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small-size exercise of round 2's new kernels for compute-sanitizer (memcheck / racecheck): TF_PEERS tile variants
-(sa_ntt_multi), PDL launches, the subproduct tree (k_tree_*), sa_push, the FRI commit (per-round and - under a tool
+(sa_ntt_multi), PDL launches, the subproduct tree (k_tree_*), the walk down it (sa_poly_eval_mode 2), sa_push, the FRI commit (per-round and - under a tool
 the start-up probe refuses it - the tail kernel path), device lists.  Every result is checked against the oracle."""
 import ctypes
 import os
@@ -52,6 +52,14 @@ for k in (600, 1024, 1100):
         got = down(eng.interpolate(up(dom), up(vals)))
         assert (got == O.interpolate_np(dom, vals)).all()
 print("tree ok", flush=True)
+
+# multi-point evaluation by the walk down the transposed tree (k_series_*, k_eval_*, k_tree_down*): ragged and full
+# trees, fewer / more coefficients than points
+for k, ncoef in ((1, 1), (5, 3), (64, 64), (100, 257), (600, 599), (1030, 2100)):
+    pts, coeffs = rand(90 + k, k), rand(91 + k, ncoef)
+    got = down(eng.poly_eval(up(coeffs), up(pts), mode=2))
+    assert (got == O.poly_eval_np(coeffs, pts)).all(), (k, ncoef)
+print("walk ok", flush=True)
 
 # push kernel
 src = up(rand(5, 1000))
