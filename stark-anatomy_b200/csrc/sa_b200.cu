@@ -1143,7 +1143,10 @@ static int launch_tile_shape(const TileArgs &a, cudaStream_t st) {
         // (a LONE 2^20 transform is one partial wave per pass: 256 tiles on 2 x 148 slots, 108 SMs carry 8 columns
         // and 40 carry 4.  Seven-column tiles - 147 CTAs of 448 threads, one per SM, every SM the same 7 columns -
         // were built, emulated bit-exact and measured: 70 us against 60 us.  One 14-warp CTA per SM whose warps
-        // all sit in the same phase loses more than the balance gains; profiles/r02q_lone_tiles.jsonl.)
+        // all sit in the same phase loses more than the balance gains; profiles/r02q_lone_tiles.jsonl.  So was a grid
+        // of exactly two CTAs per SM, 136 four-column and 160 three-column tiles in one launch (no SM above 7
+        // columns): 64.6 us against 58.7 us, profiles/r02v_lone_mix.jsonl - a lone pass is bound by the latency of a
+        // tile's own dependent phases, not by the busiest SM's column count.)
         return launch_tile<LOGL, 4, 4>(a, st);
     }
     return launch_tile<LOGL, 4, 8>(a, st);

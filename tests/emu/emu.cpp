@@ -57,6 +57,7 @@ static void run_tiles_shape(const TileArgs &a) {
     if (g_elog == 3 && g_c == 2) return run_tiles<LOGL, 3, 2>(a);
     if (g_elog == 4 && g_c == 4) return run_tiles<LOGL, 4, 4>(a);
     if (g_elog == 4 && g_c == 2) return run_tiles<LOGL, 4, 2>(a);
+    if (g_elog == 4 && g_c == 3) return run_tiles<LOGL, 4, 3>(a);  // another non-power-of-two width (48-byte rows)
     if (g_elog == 4 && g_c == 7) return run_tiles<LOGL, 4, 7>(a);  // a non-power-of-two width (ragged: 1024 = 146 * 7 + 2)
     return run_tiles<LOGL, 4, 8>(a);
 }

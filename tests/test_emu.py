@@ -44,7 +44,7 @@ def test_portable_field(E):
         assert (int(out[0]) | (int(out[1]) << 64)) == O.inverse(a)
 
 
-@pytest.mark.parametrize("shape", [(4, 8), (4, 4), (4, 2), (3, 8), (3, 4), (3, 2), (4, 7)])
+@pytest.mark.parametrize("shape", [(4, 8), (4, 4), (4, 2), (3, 8), (3, 4), (3, 2), (4, 7), (4, 3)])
 @pytest.mark.parametrize("logn", list(range(0, 14)))
 def test_tile_ntt_all_sizes(E, logn, shape):
     E.emu_set_shape(*shape)
