@@ -214,12 +214,21 @@ def allgather_leg(eng, dist, rank, world, w, reps=20):
     check = sorted({BATCH - 1, BATCH // 2, 0})
     want = {b: O.ntt_np(w, xg[b * N:(b + 1) * N].cpu().numpy().view(np.uint64), parallel=True) for b in check} if rank == 0 else {}
     stream = torch.cuda.current_stream()
-    for mode in ("nccl", "nccl-pipelined", "p2p-copy", "p2p-store", "p2p-push"):  # (the plain ones first: a fault in a peer mode cannot hide them)
+    modes = ["nccl", "nccl-pipelined", "p2p-copy", "p2p-store", "p2p-push"]  # (the plain ones first: a fault in a peer mode cannot hide them)
+    mcast = None
+    if os.environ.get("SA_BENCH_NVLS") == "1":  # NVLS multicast stores (measured slower than unicast: opt-in)
+        try:
+            mcast = sa_dist.McastBuffers(BATCH * N)
+            modes += ["nvls-store", "nvls-push"]
+        except Exception as exc:
+            res["mcast_buffers_error"] = repr(exc)[:300]
+    for mode in modes:
         if mode.startswith("p2p") and peers is None:
             continue
+        bufs = mcast if mode.startswith("nvls") else peers
         try:
             def call():
-                return sa_dist.sharded_ntt(xg, LOG_N, w, assemble=mode, peers=peers)
+                return sa_dist.sharded_ntt(xg, LOG_N, w, assemble=mode, peers=bufs)
             for _ in range(3):
                 full = call()
             torch.cuda.synchronize()
@@ -244,11 +253,12 @@ def allgather_leg(eng, dist, rank, world, w, reps=20):
         except Exception as exc:
             res["modes"][mode] = {"error": repr(exc)[:300]}
             torch.cuda.synchronize()
-    if peers is not None:
-        try:
-            peers.close()
-        except Exception:
-            pass
+    for b_ in (peers, mcast):
+        if b_ is not None:
+            try:
+                b_.close()
+            except Exception:
+                pass
     ok = {m: v["ms_per_call"] for m, v in res["modes"].items() if "ms_per_call" in v}
     if ok:
         best = min(ok, key=ok.get)
