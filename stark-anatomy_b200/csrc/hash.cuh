@@ -96,11 +96,43 @@ void blake2b_single_block(uint64_t out[8], const uint64_t m[16], uint32_t len) {
 // str(value).encode(): decimal ASCII, most significant digit first, no leading
 // zeros ("0" for zero), packed little-endian into w[0..4] (40 bytes, zero padded).
 // Returns the length in bytes (1..39).   code/algebra.py:53-57
+//
+// Round 2's second version (the first one, 650 instructions of a leaf's 2 650, divided by 1e9 with 64-bit integer
+// reciprocals and peeled 39 digits off with /10, one compare and one byte insertion each - all on the ALU pipe, the
+// one blake2b saturates).  Now: base-1e8 limbs, so that a limb is two 4-digit groups = two aligned 32-bit words of
+// the output; the long division estimates each quotient word with the FP64 unit (idle in this kernel) from BELOW and
+// repairs it with one compare; a 4-digit group becomes four ASCII bytes with multiplies (the FMA pipe, idle too);
+// the length comes from the top non-zero limb instead of from every digit.
+
+// quotient and remainder of rem_in * 2^32 + lo by 1e8 (rem_in < 1e8, so the quotient fits 32 bits).
+// K = 1e-8 (1 - 1e-13): the estimate cur * K is below the true quotient q by less than 2^32 * 1.01e-13 + rounding
+// (three roundings of 2^-53 relative) < 1e-3, so its integer part is q or q - 1: one repair step, never an overflow.
+SA_HD uint32_t dec_div_1e8(uint32_t rem_in, uint32_t lo, uint32_t &rem_out) {
+    const uint64_t cur = ((uint64_t)rem_in << 32) | lo;
+    uint32_t d = (uint32_t)((double)cur * 9.999999999999e-9);
+    uint32_t r = lo - d * 100000000u;  // cur - d * 1e8 in [0, 2e8): the low word is the whole value
+    if (r >= 100000000u) {
+        d++;
+        r -= 100000000u;
+    }
+    rem_out = r;
+    return d;
+}
+// v < 10000 -> its four decimal digits as ASCII, most significant digit in the low byte.
+// (v * 5243) >> 19 = v / 100 for v < 43699, (x * 205) >> 11 = x / 10 for x < 1029; a pair "ab" of x = 10 a + b is
+// a + 256 b = 256 x - 2559 a, and the two '0' offsets ride along in the same multiply-add.
+SA_HD uint32_t dec4_ascii(uint32_t v) {
+    const uint32_t d = (v * 5243u) >> 19, r = v - d * 100u;
+    const uint32_t td = (d * 205u) >> 11, tr = (r * 205u) >> 11;
+    const uint32_t pd = d * 256u + 0x3030u - td * 2559u;
+    const uint32_t pr = r * 256u + 0x3030u - tr * 2559u;
+    return pd + (pr << 16);
+}
 SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
-    // base-1e9 limbs, least significant first; 2^128 < 1e39 so five limbs (9,9,9,9,3 digits).
-    // After k limbs have been taken off, the quotient is below 2^128 / 1e9^k = 2^98.1, 2^68.2, 2^38.3, 2^8.4:
-    // its top words are known to be zero, so the long divisions run over 4, 4, 3 and 2 words and the last limb
-    // is the remaining quotient itself (13 divisions by a constant instead of 20).
+    // base-1e8 limbs, least significant first; 2^128 < 1e40, so five limbs of eight digits.  After k limbs have been
+    // taken off, the quotient is below 2^128 / 1e8^k = 2^101.5, 2^74.9, 2^48.3, 2^21.7: the long divisions run over
+    // 4, 4, 3 and 2 words and the last limb is the remaining quotient itself.  The first word of every long division
+    // has no remainder coming in: a 32-bit division by a constant.
     uint32_t q[4] = {x.v[0], x.v[1], x.v[2], x.v[3]};
     uint32_t chunk[5];
 #if defined(__CUDA_ARCH__)
@@ -108,70 +140,68 @@ SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
 #endif
     for (int k = 0; k < 4; k++) {
         const int top = k <= 1 ? 3 : (k == 2 ? 2 : 1);
-        uint64_t rem = 0;
+        uint32_t rem = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int i = 3; i >= 0; i--) {
             if (i > top) continue;
-            const uint64_t cur = (rem << 32) | q[i];
-            const uint64_t d = cur / 1000000000ULL;
-            q[i] = (uint32_t)d;
-            rem = cur - d * 1000000000ULL;
+            if (i == top) {
+                const uint32_t d = q[i] / 100000000u;
+                rem = q[i] - d * 100000000u;
+                q[i] = d;
+            } else {
+                q[i] = dec_div_1e8(rem, q[i], rem);
+            }
         }
-        chunk[k] = (uint32_t)rem;
+        chunk[k] = rem;
     }
-    chunk[4] = q[0];  // < 341
-    // 48 character slots, right aligned: slots 3..47 hold the 45 zero-padded digits
-    // (slot index = byte index in the 6-word buffer below)
-    uint64_t buf[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t nd = 1;  // significant digits
+    chunk[4] = q[0];  // < 3 402 824
+    // the 40-character zero-padded string, most significant limb first: word j = limb 4 - j
+    uint64_t t[6];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 5; k++) {
-        uint32_t cval = chunk[k];
+    for (int j = 0; j < 5; j++) {
+        const uint32_t c = chunk[4 - j];
+        const uint32_t hi4 = c / 10000u, lo4 = c - hi4 * 10000u;
+        t[j] = (uint64_t)dec4_ascii(hi4) | ((uint64_t)dec4_ascii(lo4) << 32);
+    }
+    t[5] = 0;
+    // significant digits: eight per limb below the top non-zero one plus that limb's own
+    uint32_t kt = 0, v = chunk[0];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < 9; j++) {
-            if (k == 4 && j >= 3) continue;  // the top limb has three digits
-            const uint32_t nq = cval / 10u;
-            const uint32_t dig = cval - nq * 10u;
-            cval = nq;
-            const int pos = 9 * k + j;  // decimal position, 0 = units
-            if (dig != 0) nd = (uint32_t)pos + 1;
-            const int slot = 47 - pos;
-            buf[slot >> 3] |= (uint64_t)(dig + 48u) << (8 * (slot & 7));
+    for (int k = 1; k < 5; k++) {
+        if (chunk[k] != 0) {
+            kt = (uint32_t)k;
+            v = chunk[k];
         }
     }
-    // drop the leading (48 - nd) bytes: out byte i = buf byte (48 - nd + i)
-    const uint32_t lz = 48u - nd;
+    const uint32_t nd = 8u * kt + 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) +
+                        (v >= 1000000u) + (v >= 10000000u);
+    // drop the leading (40 - nd) bytes: out byte i = string byte (40 - nd + i); the tail fills with zeros
+    const uint32_t lz = 40u - nd;
     const uint32_t ws = lz >> 3, bs = (lz & 7u) * 8u;
-    uint64_t t[7];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 6; i++) t[i] = buf[i];
-    t[6] = 0;
-    // whole-word shift by ws in {0..5} as three conditional stages (1, 2, 4 words)
+    // whole-word shift by ws in {0..4} as three conditional stages (1, 2, 4 words)
     if (ws & 1u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int i = 0; i < 6; i++) t[i] = t[i + 1];
+        for (int i = 0; i < 5; i++) t[i] = t[i + 1];
     }
     if (ws & 2u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int i = 0; i < 6; i++) t[i] = (i + 2 < 7) ? t[i + 2] : 0;
+        for (int i = 0; i < 5; i++) t[i] = (i + 2 < 6) ? t[i + 2] : 0;
     }
     if (ws & 4u) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int i = 0; i < 6; i++) t[i] = (i + 4 < 7) ? t[i + 4] : 0;
+        for (int i = 0; i < 5; i++) t[i] = (i + 4 < 6) ? t[i + 4] : 0;
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -181,7 +211,6 @@ SA_HD uint32_t fe_decimal_words(uint64_t w[5], const fe &x) {
         const uint64_t hi = bs ? (t[i + 1] << (64u - bs)) : 0;
         w[i] = lo | hi;
     }
-    // bytes at and beyond nd must be zero (they are: the buffer ends at slot 47)
     return nd;
 }
 

@@ -107,6 +107,14 @@ def test_decimal_and_leaf(E):
             10**38, P - 1, P - 2, 2**32 - 1, 2**32, 2**64 - 1, 2**64, 2**96 - 1, 2**96, 2**127, 10**9 * (2**32 - 1),
             (10**9 - 1) * 10**27 + 5, 2**128 - 1, 340 * 10**36] + [rng.randrange(P) for _ in range(500)] + \
            [rng.randrange(10**k) for k in range(1, 39) for _ in range(10)]
+    # base-1e8 limb boundaries (the quotient estimate of the long division is repaired by one compare: values
+    # whose limbs are 0, 1, 1e8 - 1 and whose partial quotients sit next to a multiple of 1e8), 2^32 - 1 quotients
+    edge = [0, 1, 10**8 - 1]
+    vals += [a + b * 10**8 + c * 10**16 + d * 10**24 + e * 10**32
+             for a in edge for b in edge for c in edge for d in edge for e in (0, 1, 3402822)]
+    vals += [m * 10**8 * 2**(32 * j) + off for m in (1, 2**32 - 1, 99999999) for j in (0, 1, 2)
+             for off in (-1, 0, 1) if 0 <= m * 10**8 * 2**(32 * j) + off < 2**128]
+    vals += [rng.randrange(2**128) for _ in range(3000)] + [rng.randrange(2**(8 * k)) for k in range(1, 17) for _ in range(50)]
     for v in vals:
         buf = np.zeros(40, dtype=np.uint8)
         n = E.emu_decimal(O._ptr(buf), O._ptr(O._fe(v)))
