@@ -41,6 +41,19 @@ def _worker(rank, world, port, batch, log_n, q):
     ok = bool((full == want).all()) and bool((local == want[lo * n:hi * n]).all())
     back = sa_dist.sharded_ntt(full, log_n, w, inverse=True)
     ok = ok and bool((back == x).all())
+    # the peer-buffer modes refuse to run without their buffers (and a mode's buffers must be of its kind)
+    if batch % world == 0:
+        for mode in ("p2p-store", "p2p-push", "p2p-copy", "nvls-store", "nvls-push"):
+            try:
+                sa_dist.sharded_ntt(x, log_n, w, assemble=mode)
+                ok = False
+            except ValueError as exc:
+                ok = ok and "needs peers" in str(exc)
+        try:
+            sa_dist.sharded_ntt(x, log_n, w, assemble="nvls-store", peers=object())
+            ok = False
+        except (ValueError, AttributeError):
+            pass
     roots = sa_dist.sharded_merkle_roots(x, n)
     ok = ok and roots == [O.merkle_root_np(x[b * n:(b + 1) * n]) for b in range(batch)]
     # independent FRI instances: every rank commits its shard, the transcripts are gathered
